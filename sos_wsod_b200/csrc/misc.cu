@@ -1,0 +1,163 @@
+// Error plumbing of the C ABI plus the small HBM-bound helpers around the GEMMs: fp32 -> bf16 cast (with
+// optional per-column scale and transposed copy), bf16 transpose, column sums (bias gradients).
+#include <stdarg.h>
+
+#include "common.cuh"
+
+namespace soswsod {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+constexpr int kTile = 64;
+
+// in fp32 [rows, ld_in] -> out bf16 [rows, ld_out] and/or out_t bf16 [cols, ld_out_t]; 64x64 tiles, 256 threads.
+__global__ void __launch_bounds__(256)
+cast_f32_bf16_kernel(const float* __restrict__ in, long long ld_in, int rows, int cols,
+                     const float* __restrict__ col_scale, __nv_bfloat16* __restrict__ out, long long ld_out,
+                     __nv_bfloat16* __restrict__ out_t, long long ld_out_t) {
+    __shared__ __nv_bfloat16 tile[kTile][kTile + 2];
+    const int r0 = blockIdx.y * kTile, c0 = blockIdx.x * kTile;
+    const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;  // 64 x 4
+    const int c = c0 + tx;
+    const float s = (col_scale && c < cols) ? col_scale[c] : 1.f;
+    for (int i = ty; i < kTile; i += 4) {
+        const int r = r0 + i;
+        __nv_bfloat16 v = __float2bfloat16_rn(0.f);
+        if (r < rows && c < cols) {
+            v = __float2bfloat16_rn(in[(size_t)r * ld_in + c] * s);
+            if (out) out[(size_t)r * ld_out + c] = v;
+        }
+        tile[i][tx] = v;
+    }
+    if (!out_t) return;
+    __syncthreads();
+    const int r = r0 + tx;
+    for (int i = ty; i < kTile; i += 4) {
+        const int cc = c0 + i;
+        if (r < rows && cc < cols) out_t[(size_t)cc * ld_out_t + r] = tile[tx][i];
+    }
+}
+
+__global__ void __launch_bounds__(256)
+transpose_bf16_kernel(const __nv_bfloat16* __restrict__ in, long long ld_in, int rows, int cols,
+                      __nv_bfloat16* __restrict__ out_t, long long ld_out_t) {
+    __shared__ __nv_bfloat16 tile[kTile][kTile + 2];
+    const int r0 = blockIdx.y * kTile, c0 = blockIdx.x * kTile;
+    const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
+    for (int i = ty; i < kTile; i += 4) {
+        const int r = r0 + i, c = c0 + tx;
+        tile[i][tx] = (r < rows && c < cols) ? in[(size_t)r * ld_in + c] : __float2bfloat16_rn(0.f);
+    }
+    __syncthreads();
+    const int r = r0 + tx;
+    for (int i = ty; i < kTile; i += 4) {
+        const int cc = c0 + i;
+        if (r < rows && cc < cols) out_t[(size_t)cc * ld_out_t + r] = tile[tx][i];
+    }
+}
+
+// out[c] = sum_r in[r, c]; block = 32 columns x 32 row lanes, fixed summation order (deterministic).
+template <typename T>
+__global__ void __launch_bounds__(1024)
+colsum_kernel(const T* __restrict__ in, long long ld_in, int rows, int cols, float* __restrict__ out) {
+    __shared__ float part[32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + tx;
+    float acc = 0.f;
+    if (c < cols) {
+        for (int r = ty; r < rows; r += 32) {
+            if (sizeof(T) == 2)
+                acc += __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(&in[(size_t)r * ld_in + c]));
+            else
+                acc += *reinterpret_cast<const float*>(&in[(size_t)r * ld_in + c]);
+        }
+    }
+    part[ty][tx] = acc;
+    __syncthreads();
+    if (ty == 0 && c < cols) {
+        float s = 0.f;
+        for (int i = 0; i < 32; ++i) s += part[i][tx];
+        out[c] = s;
+    }
+}
+
+// SGD with momentum and weight decay (torch.optim.SGD semantics, as built by uwsod/detectron2/solver/build.py:
+// g = grad*grad_scale + wd*p ; buf = momentum*buf + g ; p -= lr*buf), fused with the refresh of the bf16 GEMM
+// operand copy of the parameter.
+__global__ void sgd_step_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ buf, long long n,
+                                float lr, float momentum, float wd, float gscale, __nv_bfloat16* __restrict__ p_bf16) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float pv = p[i];
+    const float gv = g[i] * gscale + wd * pv;
+    const float b = momentum * buf[i] + gv;
+    buf[i] = b;
+    const float np = pv - lr * b;
+    p[i] = np;
+    if (p_bf16) p_bf16[i] = __float2bfloat16_rn(np);
+}
+
+}  // namespace soswsod
+
+using namespace soswsod;
+
+extern "C" int soswsod_sgd_step(float* param, const float* grad, float* momentum_buf, long long n, float lr,
+                                float momentum, float weight_decay, float grad_scale, void* param_bf16,
+                                soswsod_stream_t stream) {
+    SOSWSOD_CHECK_ARG(param && grad && momentum_buf && n > 0, "sgd_step: bad arguments");
+    sgd_step_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(param, grad, momentum_buf, n, lr, momentum,
+                                                                                weight_decay, grad_scale,
+                                                                                (__nv_bfloat16*)param_bf16);
+    SOSWSOD_CHECK_LAUNCH();
+    return SOSWSOD_OK;
+}
+
+extern "C" int soswsod_abi_version(void) { return SOSWSOD_ABI_VERSION; }
+extern "C" const char* soswsod_last_error(void) { return g_err; }
+
+extern "C" int soswsod_cast_f32_bf16(const float* in, long long ld_in, int rows, int cols, const float* col_scale,
+                                     void* out, long long ld_out, void* out_t, long long ld_out_t,
+                                     soswsod_stream_t stream) {
+    SOSWSOD_CHECK_ARG(in && (out || out_t), "cast_f32_bf16: null pointer");
+    SOSWSOD_CHECK_ARG(rows > 0 && cols > 0 && ld_in >= cols, "cast_f32_bf16: bad shape");
+    SOSWSOD_CHECK_ARG(!out || ld_out >= cols, "cast_f32_bf16: ld_out too small");
+    SOSWSOD_CHECK_ARG(!out_t || ld_out_t >= rows, "cast_f32_bf16: ld_out_t too small");
+    dim3 grid((cols + kTile - 1) / kTile, (rows + kTile - 1) / kTile);
+    cast_f32_bf16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(in, ld_in, rows, cols, col_scale,
+                                                                 (__nv_bfloat16*)out, ld_out, (__nv_bfloat16*)out_t,
+                                                                 ld_out_t);
+    SOSWSOD_CHECK_LAUNCH();
+    return SOSWSOD_OK;
+}
+
+extern "C" int soswsod_transpose_bf16(const void* in, long long ld_in, int rows, int cols, void* out_t,
+                                      long long ld_out_t, soswsod_stream_t stream) {
+    SOSWSOD_CHECK_ARG(in && out_t, "transpose_bf16: null pointer");
+    SOSWSOD_CHECK_ARG(rows > 0 && cols > 0 && ld_in >= cols && ld_out_t >= rows, "transpose_bf16: bad shape");
+    dim3 grid((cols + kTile - 1) / kTile, (rows + kTile - 1) / kTile);
+    transpose_bf16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)in, ld_in, rows, cols,
+                                                                  (__nv_bfloat16*)out_t, ld_out_t);
+    SOSWSOD_CHECK_LAUNCH();
+    return SOSWSOD_OK;
+}
+
+extern "C" int soswsod_colsum(const void* in, int in_dtype, long long ld_in, int rows, int cols, float* out,
+                              soswsod_stream_t stream) {
+    SOSWSOD_CHECK_ARG(in && out, "colsum: null pointer");
+    SOSWSOD_CHECK_ARG(rows > 0 && cols > 0 && ld_in >= cols, "colsum: bad shape");
+    SOSWSOD_CHECK_ARG(in_dtype == SOSWSOD_DTYPE_F32 || in_dtype == SOSWSOD_DTYPE_BF16, "colsum: bad dtype");
+    const int grid = (cols + 31) / 32;
+    if (in_dtype == SOSWSOD_DTYPE_BF16)
+        colsum_kernel<__nv_bfloat16><<<grid, 1024, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)in, ld_in, rows, cols, out);
+    else
+        colsum_kernel<float><<<grid, 1024, 0, (cudaStream_t)stream>>>((const float*)in, ld_in, rows, cols, out);
+    SOSWSOD_CHECK_LAUNCH();
+    return SOSWSOD_OK;
+}

@@ -1,0 +1,466 @@
+// ROI max-pool forward / backward for sm_100a (kernel (1) of the hot path).
+//
+// Forward: a CTA stages CT channel planes of one image in shared memory (fp32, exact), then its warps
+// walk the ROIs of the CTA's chunk independently.  Inside a warp the 32 lanes are CT channels x S
+// sub-lanes (S = 32/CT); plane stride == S (mod 32) makes every shared-memory read conflict-free.
+// Results of one ROI (CT*PH*PW values + argmax) are staged per warp and written out coalesced, as raw
+// fp32 (bit-equal to torchvision), as argmax (int32 / uint16) and as the bf16 fc6 operand already
+// multiplied by (objectness + 1).
+//
+// Backward: a CTA owns ONE (image, channel) plane; each of its warps owns a private shared-memory copy
+// of the plane and a contiguous chunk of the ROIs.  Lanes take consecutive (roi, bin) entries; entries
+// of a warp step that hit the same cell are serialised by __match_any_sync rounds, so there is no
+// atomic anywhere and the summation order is fixed (deterministic).  The private planes are summed in
+// warp order and the result overwrites grad_feat.
+//
+// Bin arithmetic follows torchvision roi_pool exactly (restated in-repo by the reference at
+// uwsod/projects/WSL/wsl/layers/csrc/ROILoopPool/ROILoopPool_cuda.cu:77-137): C round() of the fp32
+// product, fp32 bin size, floor/ceil, clamp, strict '>' scan in row-major order, empty bin -> (0, -1).
+#include "common.cuh"
+
+namespace soswsod {
+
+constexpr int kFwdThreads = 512;
+constexpr int kFwdWarps = kFwdThreads / 32;
+constexpr int kMaxBins = 256;  // PH*PW limit
+
+struct RoiGeom {
+    int batch, rs_w, rs_h;
+    float bin_w, bin_h;
+};
+
+__device__ __forceinline__ RoiGeom roi_geometry(const float* __restrict__ roi, float scale, int PH, int PW) {
+    RoiGeom g;
+    g.batch = (int)roi[0];
+    g.rs_w = (int)roundf(__fmul_rn(roi[1], scale));
+    g.rs_h = (int)roundf(__fmul_rn(roi[2], scale));
+    const int re_w = (int)roundf(__fmul_rn(roi[3], scale));
+    const int re_h = (int)roundf(__fmul_rn(roi[4], scale));
+    const int roi_w = max(re_w - g.rs_w + 1, 1);
+    const int roi_h = max(re_h - g.rs_h + 1, 1);
+    g.bin_h = __fdiv_rn((float)roi_h, (float)PH);
+    g.bin_w = __fdiv_rn((float)roi_w, (float)PW);
+    return g;
+}
+
+template <int CT>
+__global__ void __launch_bounds__(kFwdThreads, 1)
+roi_pool_fwd_kernel(const float* __restrict__ feat, int C, int H, int W, const float* __restrict__ rois, int R,
+                    int PH, int PW, float scale, const float* __restrict__ row_scale, float row_scale_bias,
+                    float* __restrict__ out_f32, int32_t* __restrict__ argmax_i32,
+                    uint16_t* __restrict__ argmax_u16, __nv_bfloat16* __restrict__ out_bf16, long long ld_bf16,
+                    int plane_stride, int rois_per_cta) {
+    constexpr int S = 32 / CT;
+    extern __shared__ __align__(16) float smem[];
+    float* planes = smem;                                        // [CT][plane_stride]
+    const int PP = PH * PW;
+    float* stage_val = planes + CT * plane_stride;               // [kFwdWarps][CT*PP]
+    int* stage_idx = reinterpret_cast<int*>(stage_val + kFwdWarps * CT * PP);
+
+    const int groups = C / CT;
+    const int b = blockIdx.x / groups;
+    const int c0 = (blockIdx.x % groups) * CT;
+    const int HW = H * W;
+
+    // ---- stage CT planes (coalesced; 128-bit when the plane is 16B-aligned) ----
+    {
+        const float* src = feat + ((size_t)b * C + c0) * HW;
+        if ((HW & 3) == 0 && ((reinterpret_cast<uintptr_t>(src) & 15) == 0) && (plane_stride & 3) == 0) {
+            const int n4 = HW >> 2;
+            for (int c = 0; c < CT; ++c) {
+                const float4* s4 = reinterpret_cast<const float4*>(src + (size_t)c * HW);
+                float4* d4 = reinterpret_cast<float4*>(planes + c * plane_stride);
+                for (int i = threadIdx.x; i < n4; i += kFwdThreads) d4[i] = __ldg(s4 + i);
+            }
+        } else {
+            for (int c = 0; c < CT; ++c)
+                for (int i = threadIdx.x; i < HW; i += kFwdThreads)
+                    planes[c * plane_stride + i] = __ldg(src + (size_t)c * HW + i);
+        }
+    }
+    __syncthreads();
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int cl = lane % CT;  // channel inside the group
+    const int sj = lane / CT;  // sub-lane inside the bin
+    const float* pl = planes + cl * plane_stride;
+    float* sv = stage_val + warp * CT * PP;
+    int* si = stage_idx + warp * CT * PP;
+    const int n_out = CT * PP;
+
+    const int r_begin = blockIdx.y * rois_per_cta;
+    const int r_end = min(R, r_begin + rois_per_cta);
+    for (int r = r_begin + warp; r < r_end; r += kFwdWarps) {
+        const RoiGeom g = roi_geometry(rois + (size_t)r * 5, scale, PH, PW);
+        if (g.batch != b) continue;  // warp-uniform
+        for (int ph = 0; ph < PH; ++ph) {
+            int hs = (int)floorf(__fmul_rn((float)ph, g.bin_h));
+            int he = (int)ceilf(__fmul_rn((float)(ph + 1), g.bin_h));
+            hs = min(max(hs + g.rs_h, 0), H);
+            he = min(max(he + g.rs_h, 0), H);
+            for (int pw = 0; pw < PW; ++pw) {
+                int ws = (int)floorf(__fmul_rn((float)pw, g.bin_w));
+                int we = (int)ceilf(__fmul_rn((float)(pw + 1), g.bin_w));
+                ws = min(max(ws + g.rs_w, 0), W);
+                we = min(max(we + g.rs_w, 0), W);
+                const bool empty = (he <= hs) || (we <= ws);
+                float m = -FLT_MAX;
+                int idx = -1;
+                for (int h = hs; h < he; ++h) {
+                    const int rowoff = h * W;
+                    for (int w = ws + sj; w < we; w += S) {
+                        const float v = pl[rowoff + w];
+                        if (v > m) {
+                            m = v;
+                            idx = rowoff + w;
+                        }
+                    }
+                }
+#pragma unroll
+                for (int off = CT; off < 32; off <<= 1) {
+                    const float om = __shfl_xor_sync(FULL_MASK, m, off);
+                    const int oi = __shfl_xor_sync(FULL_MASK, idx, off);
+                    if (om > m || (om == m && (unsigned)oi < (unsigned)idx)) {
+                        m = om;
+                        idx = oi;
+                    }
+                }
+                if (sj == 0) {
+                    sv[cl * PP + ph * PW + pw] = empty ? 0.f : m;
+                    si[cl * PP + ph * PW + pw] = idx;
+                }
+            }
+        }
+        __syncwarp();
+        const size_t obase = ((size_t)r * C + c0) * PP;
+        if (out_f32)
+            for (int i = lane; i < n_out; i += 32) out_f32[obase + i] = sv[i];
+        if (argmax_i32)
+            for (int i = lane; i < n_out; i += 32) argmax_i32[obase + i] = si[i];
+        if (argmax_u16)
+            for (int i = lane; i < n_out; i += 32) argmax_u16[obase + i] = (uint16_t)(si[i] < 0 ? 0xFFFF : si[i]);
+        if (out_bf16) {
+            const float s = row_scale ? __fadd_rn(row_scale[r], row_scale_bias) : 1.f;
+            __nv_bfloat16* dst = out_bf16 + (size_t)r * ld_bf16 + (size_t)c0 * PP;
+            if ((n_out & 1) == 0 && ((reinterpret_cast<uintptr_t>(dst) & 3) == 0)) {
+                __nv_bfloat162* d2 = reinterpret_cast<__nv_bfloat162*>(dst);
+                for (int i = lane; i < (n_out >> 1); i += 32)
+                    d2[i] = __floats2bfloat162_rn(__fmul_rn(sv[2 * i], s), __fmul_rn(sv[2 * i + 1], s));
+            } else {
+                for (int i = lane; i < n_out; i += 32) dst[i] = __float2bfloat16_rn(__fmul_rn(sv[i], s));
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// Fallback for feature planes too large for shared memory: same arithmetic straight from global/L2,
+// one warp per (roi, channel).
+__global__ void roi_pool_fwd_global_kernel(const float* __restrict__ feat, int C, int H, int W,
+                                           const float* __restrict__ rois, int R, int PH, int PW, float scale,
+                                           const float* __restrict__ row_scale, float row_scale_bias,
+                                           float* __restrict__ out_f32, int32_t* __restrict__ argmax_i32,
+                                           uint16_t* __restrict__ argmax_u16,
+                                           __nv_bfloat16* __restrict__ out_bf16, long long ld_bf16) {
+    const int lane = threadIdx.x & 31;
+    const long long gw = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (gw >= (long long)R * C) return;
+    const int r = (int)(gw / C), c = (int)(gw % C);
+    const RoiGeom g = roi_geometry(rois + (size_t)r * 5, scale, PH, PW);
+    const float* pl = feat + ((size_t)g.batch * C + c) * H * W;
+    const int PP = PH * PW;
+    const float s = row_scale ? __fadd_rn(row_scale[r], row_scale_bias) : 1.f;
+    for (int bin = lane; bin < PP; bin += 32) {
+        const int ph = bin / PW, pw = bin % PW;
+        int hs = (int)floorf(__fmul_rn((float)ph, g.bin_h));
+        int he = (int)ceilf(__fmul_rn((float)(ph + 1), g.bin_h));
+        hs = min(max(hs + g.rs_h, 0), H);
+        he = min(max(he + g.rs_h, 0), H);
+        int ws = (int)floorf(__fmul_rn((float)pw, g.bin_w));
+        int we = (int)ceilf(__fmul_rn((float)(pw + 1), g.bin_w));
+        ws = min(max(ws + g.rs_w, 0), W);
+        we = min(max(we + g.rs_w, 0), W);
+        const bool empty = (he <= hs) || (we <= ws);
+        float m = empty ? 0.f : -FLT_MAX;
+        int idx = -1;
+        for (int h = hs; h < he; ++h)
+            for (int w = ws; w < we; ++w) {
+                const float v = __ldg(pl + h * W + w);
+                if (v > m) {
+                    m = v;
+                    idx = h * W + w;
+                }
+            }
+        const size_t o = ((size_t)r * C + c) * PP + bin;
+        if (out_f32) out_f32[o] = m;
+        if (argmax_i32) argmax_i32[o] = idx;
+        if (argmax_u16) argmax_u16[o] = (uint16_t)(idx < 0 ? 0xFFFF : idx);
+        if (out_bf16) out_bf16[(size_t)r * ld_bf16 + (size_t)c * PP + bin] = __float2bfloat16_rn(__fmul_rn(m, s));
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Backward
+// ------------------------------------------------------------------------------------------------
+constexpr int kBwdMaxWarps = 8;
+
+template <typename GradT, typename ArgT>
+__device__ __forceinline__ void load_entry(const GradT* __restrict__ grad, long long ld_grad,
+                                           const ArgT* __restrict__ argmax, const float* __restrict__ rois,
+                                           const float* __restrict__ row_scale, float row_scale_bias, int N,
+                                           int b, int c, int C, int PP, long long i, long long total, int r0,
+                                           int& a, float& gval) {
+    a = -1;
+    gval = 0.f;
+    if (i >= total) return;
+    const int r = r0 + (int)(i / PP);
+    const int bin = (int)(i % PP);
+    if (N > 1 && (int)rois[(size_t)r * 5] != b) return;
+    const ArgT raw = argmax[((size_t)r * C + c) * PP + bin];
+    int av;
+    if (sizeof(ArgT) == 2)
+        av = ((unsigned)raw == 0xFFFFu) ? -1 : (int)(unsigned)raw;
+    else
+        av = (int)raw;
+    if (av < 0) return;
+    a = av;
+    float gv;
+    if (sizeof(GradT) == 2)
+        gv = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(&grad[(size_t)r * ld_grad + (size_t)c * PP + bin]));
+    else
+        gv = *reinterpret_cast<const float*>(&grad[(size_t)r * ld_grad + (size_t)c * PP + bin]);
+    const float s = row_scale ? __fadd_rn(row_scale[r], row_scale_bias) : 1.f;
+    gval = gv * s;
+}
+
+template <typename GradT, typename ArgT>
+__global__ void __launch_bounds__(kBwdMaxWarps * 32, 1)
+roi_pool_bwd_kernel(const GradT* __restrict__ grad, long long ld_grad, const ArgT* __restrict__ argmax,
+                    const float* __restrict__ rois, int R, const float* __restrict__ row_scale,
+                    float row_scale_bias, int N, int C, int H, int W, int PP, float* __restrict__ grad_feat,
+                    int plane_stride) {
+    extern __shared__ __align__(16) float planes[];  // [nwarps][plane_stride]
+    const int nw = blockDim.x >> 5;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = blockIdx.x / C, c = blockIdx.x % C;
+    const int HW = H * W;
+    for (int i = threadIdx.x; i < nw * plane_stride; i += blockDim.x) planes[i] = 0.f;
+    __syncthreads();
+
+    float* my = planes + warp * plane_stride;
+    const int per = (R + nw - 1) / nw;
+    const int r0 = warp * per;
+    const int r1 = min(R, r0 + per);
+    const long long total = (r1 > r0) ? (long long)(r1 - r0) * PP : 0;
+
+    int a_nx;
+    float g_nx;
+    load_entry<GradT, ArgT>(grad, ld_grad, argmax, rois, row_scale, row_scale_bias, N, b, c, C, PP, lane, total,
+                            r0, a_nx, g_nx);
+    for (long long i0 = 0; i0 < total; i0 += 32) {
+        const int a = a_nx;
+        const float gval = g_nx;
+        // prefetch the next step's entry while this one is being applied
+        load_entry<GradT, ArgT>(grad, ld_grad, argmax, rois, row_scale, row_scale_bias, N, b, c, C, PP,
+                                i0 + 32 + lane, total, r0, a_nx, g_nx);
+        const bool valid = a >= 0;
+        const unsigned act = __ballot_sync(FULL_MASK, valid);
+        if (act == 0) continue;
+        unsigned peers = 0;
+        if (valid) peers = __match_any_sync(act, a);
+        unsigned pending = act;
+        while (pending) {
+            const bool lead = valid && ((pending >> lane) & 1u) && ((__ffs(peers & pending) - 1) == lane);
+            if (lead) my[a] += gval;
+            __syncwarp();
+            pending &= ~__ballot_sync(FULL_MASK, lead);
+        }
+    }
+    __syncthreads();
+    float* dst = grad_feat + ((size_t)b * C + c) * HW;
+    for (int i = threadIdx.x; i < HW; i += blockDim.x) {
+        float s = 0.f;
+        for (int w = 0; w < nw; ++w) s += planes[w * plane_stride + i];
+        dst[i] = s;
+    }
+}
+
+// Fallback for planes that do not fit shared memory: zero + global atomics (documented, rarely used).
+template <typename GradT, typename ArgT>
+__global__ void roi_pool_bwd_atomic_kernel(const GradT* __restrict__ grad, long long ld_grad,
+                                           const ArgT* __restrict__ argmax, const float* __restrict__ rois,
+                                           long long total, const float* __restrict__ row_scale,
+                                           float row_scale_bias, int C, int H, int W, int PP,
+                                           float* __restrict__ grad_feat) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int bin = (int)(i % PP);
+    const int c = (int)((i / PP) % C);
+    const int r = (int)(i / ((long long)PP * C));
+    const ArgT raw = argmax[i];
+    int a = (sizeof(ArgT) == 2) ? (((unsigned)raw == 0xFFFFu) ? -1 : (int)(unsigned)raw) : (int)raw;
+    if (a < 0) return;
+    float gv;
+    if (sizeof(GradT) == 2)
+        gv = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(&grad[(size_t)r * ld_grad + (size_t)c * PP + bin]));
+    else
+        gv = *reinterpret_cast<const float*>(&grad[(size_t)r * ld_grad + (size_t)c * PP + bin]);
+    const float s = row_scale ? __fadd_rn(row_scale[r], row_scale_bias) : 1.f;
+    const int b = (int)rois[(size_t)r * 5];
+    atomicAdd(grad_feat + ((size_t)b * C + c) * H * W + a, gv * s);
+}
+
+static int g_max_smem_optin = -1;
+static int g_num_sms = -1;
+static int query_device() {
+    if (g_max_smem_optin >= 0) return 0;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return -1;
+    int v = 0, s = 0;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess) return -1;
+    if (cudaDeviceGetAttribute(&s, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
+    g_num_sms = s;
+    g_max_smem_optin = v;
+    return 0;
+}
+int device_num_sms() {
+    query_device();
+    return g_num_sms > 0 ? g_num_sms : 148;
+}
+int device_max_smem() {
+    query_device();
+    return g_max_smem_optin > 0 ? g_max_smem_optin : 227 * 1024;
+}
+
+template <int CT>
+static int launch_fwd(const float* feat, int n, int c, int h, int w, const float* rois, int R, int PH, int PW,
+                      float scale, const float* row_scale, float bias, float* out_f32, int32_t* a32, uint16_t* a16,
+                      __nv_bfloat16* obf, long long ld, int plane_stride, size_t smem, cudaStream_t st) {
+    const int groups = n * (c / CT);
+    // Split the ROIs into `chunks` CTAs per channel group so that groups*chunks fills a whole number of
+    // waves of the SMs (1 CTA/SM: the planes take most of shared memory) with the smallest tail.
+    const int sms = device_num_sms();
+    const int max_chunks = max(1, min(32, (R + kFwdWarps - 1) / kFwdWarps));
+    int chunks = 1;
+    double best = 1e30;
+    for (int ch = 1; ch <= max_chunks; ++ch) {
+        const int waves = (groups * ch + sms - 1) / sms;
+        const double cost = (double)waves / ch;  // ~ time in units of "all ROIs of one group on one SM"
+        if (cost < best - 1e-9) {
+            best = cost;
+            chunks = ch;
+        }
+    }
+    const int rois_per_cta = (R + chunks - 1) / chunks;
+    chunks = (R + rois_per_cta - 1) / rois_per_cta;
+    SOSWSOD_CHECK_CUDA(cudaFuncSetAttribute(roi_pool_fwd_kernel<CT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)smem));
+    roi_pool_fwd_kernel<CT><<<dim3(groups, chunks), kFwdThreads, smem, st>>>(
+        feat, c, h, w, rois, R, PH, PW, scale, row_scale, bias, out_f32, a32, a16, obf, ld, plane_stride,
+        rois_per_cta);
+    SOSWSOD_CHECK_LAUNCH();
+    return SOSWSOD_OK;
+}
+
+}  // namespace soswsod
+
+using namespace soswsod;
+
+extern "C" int soswsod_roi_pool_forward(const float* feat, int n, int c, int h, int w, const float* rois,
+                                        int num_rois, int pooled_h, int pooled_w, float spatial_scale,
+                                        const float* row_scale, float row_scale_bias, float* out_f32,
+                                        void* argmax, int argmax_dtype, void* out_bf16, long long ld_bf16,
+                                        soswsod_stream_t stream) {
+    SOSWSOD_CHECK_ARG(feat && rois, "roi_pool_forward: null feat/rois");
+    SOSWSOD_CHECK_ARG(n > 0 && c > 0 && h > 0 && w > 0 && num_rois >= 0, "roi_pool_forward: bad shape");
+    SOSWSOD_CHECK_ARG(pooled_h > 0 && pooled_w > 0 && pooled_h * pooled_w <= kMaxBins,
+                      "roi_pool_forward: pooled size %dx%d unsupported", pooled_h, pooled_w);
+    SOSWSOD_CHECK_ARG(argmax_dtype == SOSWSOD_ARGMAX_I32 || argmax_dtype == SOSWSOD_ARGMAX_U16,
+                      "roi_pool_forward: bad argmax dtype");
+    SOSWSOD_CHECK_ARG(argmax_dtype == SOSWSOD_ARGMAX_I32 || (long long)h * w < 65535,
+                      "roi_pool_forward: uint16 argmax needs h*w < 65535");
+    SOSWSOD_CHECK_ARG(!out_bf16 || ld_bf16 >= (long long)c * pooled_h * pooled_w, "roi_pool_forward: ld_bf16 too small");
+    if (num_rois == 0) return SOSWSOD_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    int32_t* a32 = argmax_dtype == SOSWSOD_ARGMAX_I32 ? (int32_t*)argmax : nullptr;
+    uint16_t* a16 = argmax_dtype == SOSWSOD_ARGMAX_U16 ? (uint16_t*)argmax : nullptr;
+    __nv_bfloat16* obf = (__nv_bfloat16*)out_bf16;
+    const int PP = pooled_h * pooled_w;
+    const int HW = h * w;
+    const int max_smem = device_max_smem();
+    // pick the largest channel group whose planes + staging fit
+    const int cts[4] = {8, 4, 2, 1};
+    for (int k = 0; k < 4; ++k) {
+        const int CT = cts[k];
+        if (c % CT) continue;
+        const int S = 32 / CT;
+        int plane_stride = ((HW + 31) / 32) * 32 + (S % 32);
+        if (CT == 1) plane_stride = ((HW + 3) / 4) * 4;
+        const size_t smem = (size_t)CT * plane_stride * 4 + (size_t)kFwdWarps * CT * PP * 8;
+        if (smem > (size_t)max_smem) continue;
+        switch (CT) {
+            case 8: return launch_fwd<8>(feat, n, c, h, w, rois, num_rois, pooled_h, pooled_w, spatial_scale, row_scale, row_scale_bias, out_f32, a32, a16, obf, ld_bf16, plane_stride, smem, st);
+            case 4: return launch_fwd<4>(feat, n, c, h, w, rois, num_rois, pooled_h, pooled_w, spatial_scale, row_scale, row_scale_bias, out_f32, a32, a16, obf, ld_bf16, plane_stride, smem, st);
+            case 2: return launch_fwd<2>(feat, n, c, h, w, rois, num_rois, pooled_h, pooled_w, spatial_scale, row_scale, row_scale_bias, out_f32, a32, a16, obf, ld_bf16, plane_stride, smem, st);
+            default: return launch_fwd<1>(feat, n, c, h, w, rois, num_rois, pooled_h, pooled_w, spatial_scale, row_scale, row_scale_bias, out_f32, a32, a16, obf, ld_bf16, plane_stride, smem, st);
+        }
+    }
+    // plane larger than shared memory: global-memory kernel
+    const long long warps = (long long)num_rois * c;
+    const int threads = 256;
+    const long long blocks = (warps * 32 + threads - 1) / threads;
+    roi_pool_fwd_global_kernel<<<(unsigned)blocks, threads, 0, st>>>(feat, c, h, w, rois, num_rois, pooled_h,
+                                                                    pooled_w, spatial_scale, row_scale,
+                                                                    row_scale_bias, out_f32, a32, a16, obf, ld_bf16);
+    SOSWSOD_CHECK_LAUNCH();
+    return SOSWSOD_OK;
+}
+
+template <typename GradT, typename ArgT>
+static int launch_bwd(const void* grad, long long ld_grad, const void* argmax, const float* rois, int R,
+                      const float* row_scale, float bias, int n, int c, int h, int w, int PP, float* grad_feat,
+                      cudaStream_t st) {
+    const int HW = h * w;
+    const int plane_stride = ((HW + 3) / 4) * 4;
+    const int max_smem = device_max_smem();
+    int nw = max_smem / (plane_stride * 4);
+    if (nw > kBwdMaxWarps) nw = kBwdMaxWarps;
+    if (nw >= 1) {
+        const size_t smem = (size_t)nw * plane_stride * 4;
+        SOSWSOD_CHECK_CUDA(cudaFuncSetAttribute(roi_pool_bwd_kernel<GradT, ArgT>,
+                                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        roi_pool_bwd_kernel<GradT, ArgT><<<n * c, nw * 32, smem, st>>>(
+            (const GradT*)grad, ld_grad, (const ArgT*)argmax, rois, R, row_scale, bias, n, c, h, w, PP, grad_feat,
+            plane_stride);
+        SOSWSOD_CHECK_LAUNCH();
+        return SOSWSOD_OK;
+    }
+    SOSWSOD_CHECK_CUDA(cudaMemsetAsync(grad_feat, 0, (size_t)n * c * HW * 4, st));
+    const long long total = (long long)R * c * PP;
+    if (total == 0) return SOSWSOD_OK;
+    roi_pool_bwd_atomic_kernel<GradT, ArgT><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
+        (const GradT*)grad, ld_grad, (const ArgT*)argmax, rois, total, row_scale, bias, c, h, w, PP, grad_feat);
+    SOSWSOD_CHECK_LAUNCH();
+    return SOSWSOD_OK;
+}
+
+extern "C" int soswsod_roi_pool_backward(const void* grad_out, int grad_dtype, long long ld_grad,
+                                         const void* argmax, int argmax_dtype, const float* rois, int num_rois,
+                                         const float* row_scale, float row_scale_bias, int n, int c, int h, int w,
+                                         int pooled_h, int pooled_w, float* grad_feat, soswsod_stream_t stream) {
+    SOSWSOD_CHECK_ARG(grad_out && argmax && rois && grad_feat, "roi_pool_backward: null pointer");
+    SOSWSOD_CHECK_ARG(n > 0 && c > 0 && h > 0 && w > 0 && num_rois >= 0, "roi_pool_backward: bad shape");
+    SOSWSOD_CHECK_ARG(grad_dtype == SOSWSOD_DTYPE_F32 || grad_dtype == SOSWSOD_DTYPE_BF16, "roi_pool_backward: bad grad dtype");
+    SOSWSOD_CHECK_ARG(argmax_dtype == SOSWSOD_ARGMAX_I32 || argmax_dtype == SOSWSOD_ARGMAX_U16, "roi_pool_backward: bad argmax dtype");
+    const int PP = pooled_h * pooled_w;
+    SOSWSOD_CHECK_ARG(ld_grad >= (long long)c * PP, "roi_pool_backward: ld_grad too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (grad_dtype == SOSWSOD_DTYPE_F32) {
+        if (argmax_dtype == SOSWSOD_ARGMAX_I32)
+            return launch_bwd<float, int32_t>(grad_out, ld_grad, argmax, rois, num_rois, row_scale, row_scale_bias, n, c, h, w, PP, grad_feat, st);
+        return launch_bwd<float, uint16_t>(grad_out, ld_grad, argmax, rois, num_rois, row_scale, row_scale_bias, n, c, h, w, PP, grad_feat, st);
+    }
+    if (argmax_dtype == SOSWSOD_ARGMAX_I32)
+        return launch_bwd<__nv_bfloat16, int32_t>(grad_out, ld_grad, argmax, rois, num_rois, row_scale, row_scale_bias, n, c, h, w, PP, grad_feat, st);
+    return launch_bwd<__nv_bfloat16, uint16_t>(grad_out, ld_grad, argmax, rois, num_rois, row_scale, row_scale_bias, n, c, h, w, PP, grad_feat, st);
+}

@@ -1,0 +1,343 @@
+"""Tensor-level wrappers over the C ABI (include/soswsod_b200.h).  Every function takes CUDA tensors, allocates
+outputs/workspaces with torch (so the caching allocator and streams keep working), passes raw device pointers
+and the current stream, and raises RuntimeError on any failure.  No function here has a CPU path."""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import ARGMAX_I32, ARGMAX_U16, DTYPE_BF16, DTYPE_F32, check
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("sos_wsod_b200 ops run on CUDA tensors only (sm_100a); there is no CPU fallback")
+
+
+def _dt(t: torch.Tensor) -> int:
+    if t.dtype == torch.float32:
+        return DTYPE_F32
+    if t.dtype == torch.bfloat16:
+        return DTYPE_BF16
+    raise RuntimeError(f"unsupported dtype {t.dtype}")
+
+
+# ------------------------------------------------------------------------------------------------
+# (1) ROI max-pool
+# ------------------------------------------------------------------------------------------------
+def roi_pool_forward(feat: torch.Tensor, rois: torch.Tensor, pooled: Tuple[int, int] = (7, 7),
+                     spatial_scale: float = 0.125, row_scale: Optional[torch.Tensor] = None,
+                     row_scale_bias: float = 0.0, want_f32: bool = True, want_bf16: bool = False,
+                     argmax_u16: bool = False, out_bf16: Optional[torch.Tensor] = None):
+    """feat fp32 [N,C,H,W], rois fp32 [M,5] -> (out_f32 [M,C,ph,pw] | None, argmax [M,C,ph,pw], out_bf16 [M, C*ph*pw] | None).
+    out_bf16 = pooled * (row_scale + row_scale_bias), the fc6 GEMM operand."""
+    _need_cuda(feat, rois, row_scale)
+    assert feat.dtype == torch.float32 and rois.dtype == torch.float32 and rois.dim() == 2 and rois.size(1) == 5
+    feat = feat.contiguous()
+    rois = rois.contiguous()
+    n, c, h, w = feat.shape
+    m = rois.size(0)
+    ph, pw = pooled
+    out = torch.empty((m, c, ph, pw), dtype=torch.float32, device=feat.device) if want_f32 else None
+    if argmax_u16:
+        argmax = torch.empty((m, c, ph, pw), dtype=torch.int16, device=feat.device)  # bits are uint16
+    else:
+        argmax = torch.empty((m, c, ph, pw), dtype=torch.int32, device=feat.device)
+    obf = None
+    ld = 0
+    if want_bf16 or out_bf16 is not None:
+        obf = out_bf16 if out_bf16 is not None else torch.empty((m, c * ph * pw), dtype=torch.bfloat16, device=feat.device)
+        assert obf.dtype == torch.bfloat16 and obf.stride(-1) == 1
+        ld = obf.stride(0)
+    if row_scale is not None:
+        row_scale = row_scale.contiguous().float()
+    lib = _lib.load()
+    check(lib.soswsod_roi_pool_forward(_ptr(feat), n, c, h, w, _ptr(rois), m, ph, pw, float(spatial_scale),
+                                       _ptr(row_scale), float(row_scale_bias), _ptr(out), _ptr(argmax),
+                                       ARGMAX_U16 if argmax_u16 else ARGMAX_I32, _ptr(obf), ld, _stream()),
+          "roi_pool_forward")
+    return out, argmax, obf
+
+
+def roi_pool_backward(grad_out: torch.Tensor, argmax: torch.Tensor, rois: torch.Tensor, feat_shape,
+                      pooled: Tuple[int, int] = (7, 7), row_scale: Optional[torch.Tensor] = None,
+                      row_scale_bias: float = 0.0) -> torch.Tensor:
+    """grad_out [M, C*ph*pw] (or [M,C,ph,pw]) fp32/bf16 -> grad_feat fp32 [N,C,H,W] (overwritten, atomic-free)."""
+    _need_cuda(grad_out, argmax, rois)
+    n, c, h, w = feat_shape
+    ph, pw = pooled
+    m = rois.size(0)
+    if grad_out.dim() == 4:
+        grad_out = grad_out.reshape(m, -1)
+    if grad_out.stride(-1) != 1:
+        grad_out = grad_out.contiguous()
+    rois = rois.contiguous()
+    grad_feat = torch.empty((n, c, h, w), dtype=torch.float32, device=grad_out.device)
+    if m == 0:
+        return grad_feat.zero_()
+    a_dt = ARGMAX_U16 if argmax.dtype == torch.int16 else ARGMAX_I32
+    if row_scale is not None:
+        row_scale = row_scale.contiguous().float()
+    lib = _lib.load()
+    check(lib.soswsod_roi_pool_backward(_ptr(grad_out), _dt(grad_out), grad_out.stride(0), _ptr(argmax.contiguous()), a_dt,
+                                        _ptr(rois), m, _ptr(row_scale), float(row_scale_bias), n, c, h, w, ph, pw,
+                                        _ptr(grad_feat), _stream()), "roi_pool_backward")
+    return grad_feat
+
+
+# ------------------------------------------------------------------------------------------------
+# (2) GEMM + helpers
+# ------------------------------------------------------------------------------------------------
+def gemm_bf16(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool = False,
+              out_dtype: torch.dtype = torch.float32, bias: Optional[torch.Tensor] = None, relu: bool = False,
+              mask_src: Optional[torch.Tensor] = None, mask_scale: float = 1.0, dropout_p: float = 0.0,
+              dropout_seed: int = 0, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """D[M,N] = epilogue(sum_k A[m,k] B[n,k]).  a: [M,K] (a_mn False) or [K,M] (a_mn True); b likewise with N."""
+    _need_cuda(a, b, bias, mask_src, out)
+    assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16 and a.dim() == 2 and b.dim() == 2
+    assert a.stride(1) == 1 and b.stride(1) == 1
+    if a_mn:
+        k, m = a.shape
+    else:
+        m, k = a.shape
+    if b_mn:
+        kb, n = b.shape
+    else:
+        n, kb = b.shape
+    assert k == kb, f"K mismatch {k} vs {kb}"
+    if out is None:
+        out = torch.empty((m, n), dtype=out_dtype, device=a.device)
+    assert out.shape == (m, n) and out.stride(1) == 1
+    if bias is not None:
+        assert bias.dtype == torch.float32 and bias.numel() == n
+        bias = bias.contiguous()
+    ld_mask = 0
+    if mask_src is not None:
+        assert mask_src.dtype == torch.bfloat16 and mask_src.shape == (m, n) and mask_src.stride(1) == 1
+        ld_mask = mask_src.stride(0)
+    lib = _lib.load()
+    check(lib.soswsod_gemm_bf16(_ptr(a), a.stride(0), int(a_mn), _ptr(b), b.stride(0), int(b_mn), _ptr(out),
+                                out.stride(0), _dt(out), m, n, k, _ptr(bias), int(relu), _ptr(mask_src), ld_mask,
+                                float(mask_scale), float(dropout_p), int(dropout_seed) & 0xFFFFFFFFFFFFFFFF, _stream()),
+          "gemm_bf16")
+    return out
+
+
+def dropout_mask(m: int, n: int, p: float, seed: int, device="cuda") -> torch.Tensor:
+    mask = torch.empty((m, n), dtype=torch.uint8, device=device)
+    check(_lib.load().soswsod_dropout_mask(_ptr(mask), m, n, float(p), int(seed) & 0xFFFFFFFFFFFFFFFF, _stream()),
+          "dropout_mask")
+    return mask
+
+
+def cast_f32_bf16(x: torch.Tensor, col_scale: Optional[torch.Tensor] = None, want_out: bool = True,
+                  want_t: bool = False, out: Optional[torch.Tensor] = None, ld_pad: int = 8):
+    """x fp32 [rows, cols] -> (bf16 [rows, cols] | None, bf16 transposed [cols, rows_padded][:, :rows] | None)."""
+    _need_cuda(x, col_scale)
+    assert x.dtype == torch.float32 and x.dim() == 2 and x.stride(1) == 1
+    rows, cols = x.shape
+    o = None
+    if out is not None:
+        o = out
+    elif want_out:
+        o = torch.empty((rows, cols), dtype=torch.bfloat16, device=x.device)
+    ot = None
+    if want_t:
+        rp = (rows + ld_pad - 1) // ld_pad * ld_pad
+        ot = torch.zeros((cols, rp), dtype=torch.bfloat16, device=x.device)[:, :rows]
+    check(_lib.load().soswsod_cast_f32_bf16(_ptr(x), x.stride(0), rows, cols, _ptr(col_scale), _ptr(o),
+                                            0 if o is None else o.stride(0), _ptr(ot), 0 if ot is None else ot.stride(0),
+                                            _stream()), "cast_f32_bf16")
+    return o, ot
+
+
+def transpose_bf16(x: torch.Tensor, ld_pad: int = 8) -> torch.Tensor:
+    _need_cuda(x)
+    assert x.dtype == torch.bfloat16 and x.dim() == 2 and x.stride(1) == 1
+    rows, cols = x.shape
+    rp = (rows + ld_pad - 1) // ld_pad * ld_pad
+    ot = torch.zeros((cols, rp), dtype=torch.bfloat16, device=x.device)[:, :rows]
+    check(_lib.load().soswsod_transpose_bf16(_ptr(x), x.stride(0), rows, cols, _ptr(ot), ot.stride(0), _stream()),
+          "transpose_bf16")
+    return ot
+
+
+def colsum(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _need_cuda(x)
+    assert x.dim() == 2 and x.stride(1) == 1
+    rows, cols = x.shape
+    if out is None:
+        out = torch.empty((cols,), dtype=torch.float32, device=x.device)
+    check(_lib.load().soswsod_colsum(_ptr(x), _dt(x), x.stride(0), rows, cols, _ptr(out), _stream()), "colsum")
+    return out
+
+
+def sgd_step(param: torch.Tensor, grad: torch.Tensor, buf: torch.Tensor, lr: float, momentum: float,
+             weight_decay: float, grad_scale: float = 1.0, param_bf16: Optional[torch.Tensor] = None) -> None:
+    _need_cuda(param, grad, buf, param_bf16)
+    assert param.is_contiguous() and grad.is_contiguous() and buf.is_contiguous()
+    assert param.dtype == grad.dtype == buf.dtype == torch.float32
+    assert param_bf16 is None or (param_bf16.is_contiguous() and param_bf16.dtype == torch.bfloat16)
+    check(_lib.load().soswsod_sgd_step(_ptr(param), _ptr(grad), _ptr(buf), param.numel(), float(lr), float(momentum),
+                                       float(weight_decay), float(grad_scale), _ptr(param_bf16), _stream()), "sgd_step")
+
+
+# ------------------------------------------------------------------------------------------------
+# (3) WSDDN
+# ------------------------------------------------------------------------------------------------
+def wsddn_forward(logits: torch.Tensor, col_cls: int, col_det: int, num_views: int, R: int, C: int,
+                  gt_onehot: torch.Tensor, dlogits: Optional[torch.Tensor] = None):
+    """logits fp32 [V*R, ld] -> (scores [V,R,C], img_scores [V,C], loss [V]); if dlogits is given the unit-upstream
+    gradient of each view's loss is written into its cls/det column blocks."""
+    _need_cuda(logits, gt_onehot, dlogits)
+    assert logits.dtype == torch.float32 and logits.stride(1) == 1 and logits.size(0) == num_views * R
+    dev = logits.device
+    scores = torch.empty((num_views, R, C), dtype=torch.float32, device=dev)
+    img = torch.empty((num_views, C), dtype=torch.float32, device=dev)
+    loss = torch.empty((num_views,), dtype=torch.float32, device=dev)
+    gt = gt_onehot.reshape(-1).contiguous().float()
+    assert gt.numel() == C
+    check(_lib.load().soswsod_wsddn_forward(_ptr(logits), logits.stride(0), col_cls, col_det, num_views, R, C, _ptr(gt),
+                                            _ptr(scores), _ptr(img), _ptr(loss), _ptr(dlogits),
+                                            0 if dlogits is None else dlogits.stride(0), _stream()), "wsddn_forward")
+    return scores, img, loss
+
+
+# ------------------------------------------------------------------------------------------------
+# (4) OICR
+# ------------------------------------------------------------------------------------------------
+def oicr_avg_scores(wsddn_scores: torch.Tensor, logits: Optional[torch.Tensor], col_ref0: int, ref_stride: int,
+                    num_views: int, R: int, C: int, K: int) -> torch.Tensor:
+    _need_cuda(wsddn_scores, logits)
+    prev = torch.empty((K, R, C + 1), dtype=torch.float32, device=wsddn_scores.device)
+    check(_lib.load().soswsod_oicr_avg_scores(_ptr(wsddn_scores.contiguous()), _ptr(logits),
+                                              0 if logits is None else logits.stride(0), col_ref0, ref_stride,
+                                              num_views, R, C, K, _ptr(prev), _stream()), "oicr_avg_scores")
+    return prev
+
+
+def oicr_mine_label(prev: torch.Tensor, boxes: torch.Tensor, gt_classes: torch.Tensor, C: int, top_k: int,
+                    score_thr: float = 0.05, nms_thr: float = 0.01, iou_lo: float = 0.5, iou_hi: float = 0.6):
+    """prev fp32 [K,R,ld]; boxes fp32 [R,4]; gt_classes int32 [G] ascending.  Returns a dict of device tensors."""
+    _need_cuda(prev, boxes, gt_classes)
+    assert prev.dtype == torch.float32 and prev.dim() == 3 and prev.is_contiguous()
+    K, R, ld = prev.shape
+    G = gt_classes.numel()
+    gt_classes = gt_classes.to(torch.int32).contiguous()
+    boxes = boxes.contiguous()
+    dev = prev.device
+    ms = top_k * G
+    out = {
+        "seed_count": torch.zeros((K,), dtype=torch.int32, device=dev),
+        "seed_index": torch.zeros((K, ms), dtype=torch.int32, device=dev),
+        "seed_class": torch.zeros((K, ms), dtype=torch.int32, device=dev),
+        "seed_score": torch.zeros((K, ms), dtype=torch.float32, device=dev),
+        "gt_class": torch.empty((K, R), dtype=torch.int32, device=dev),
+        "gt_weight": torch.empty((K, R), dtype=torch.float32, device=dev),
+        "gt_index": torch.empty((K, R), dtype=torch.int32, device=dev),
+        "counts": torch.empty((K, 3), dtype=torch.int32, device=dev),
+    }
+    lib = _lib.load()
+    wsb = lib.soswsod_oicr_mine_workspace_bytes(top_k, G, K)
+    ws = torch.empty((wsb,), dtype=torch.uint8, device=dev)
+    check(lib.soswsod_oicr_mine_label(_ptr(prev), ld, _ptr(boxes), _ptr(gt_classes), G, R, C, K, top_k, float(score_thr),
+                                      float(nms_thr), float(iou_lo), float(iou_hi), _ptr(out["seed_count"]),
+                                      _ptr(out["seed_index"]), _ptr(out["seed_class"]), _ptr(out["seed_score"]),
+                                      _ptr(out["gt_class"]), _ptr(out["gt_weight"]), _ptr(out["gt_index"]),
+                                      _ptr(out["counts"]), _ptr(ws), wsb, _stream()), "oicr_mine_label")
+    return out
+
+
+def oicr_loss(logits: torch.Tensor, col_ref0: int, ref_stride: int, boxes: torch.Tensor, gt_class: torch.Tensor,
+              gt_weight: torch.Tensor, gt_index: torch.Tensor, num_views: int, R: int, C: int, K: int,
+              flip_quirk: bool = True, weights=(10.0, 10.0, 5.0, 5.0), dlogits: Optional[torch.Tensor] = None):
+    """Returns (losses [K,2], view_losses [K,V,2], acc_counts [K,V,5])."""
+    _need_cuda(logits, boxes, gt_class, gt_weight, gt_index, dlogits)
+    dev = logits.device
+    losses = torch.empty((K, 2), dtype=torch.float32, device=dev)
+    view_losses = torch.zeros((K, num_views, 2), dtype=torch.float32, device=dev)
+    acc = torch.zeros((K, num_views, 5), dtype=torch.int32, device=dev)
+    boxes = boxes.contiguous()
+    assert boxes.shape == (num_views, R, 4)
+    check(_lib.load().soswsod_oicr_loss(_ptr(logits), logits.stride(0), col_ref0, ref_stride, _ptr(boxes),
+                                        _ptr(gt_class), _ptr(gt_weight), _ptr(gt_index), num_views, R, C, K,
+                                        int(flip_quirk), *[float(x) for x in weights], _ptr(losses), _ptr(view_losses),
+                                        _ptr(acc), _ptr(dlogits), 0 if dlogits is None else dlogits.stride(0),
+                                        _stream()), "oicr_loss")
+    return losses, view_losses, acc
+
+
+# ------------------------------------------------------------------------------------------------
+# (5) test-time
+# ------------------------------------------------------------------------------------------------
+def predict(logits: torch.Tensor, col_ref0: int, ref_stride: int, boxes: torch.Tensor, C: int, K: int,
+            weights=(10.0, 10.0, 5.0, 5.0)):
+    _need_cuda(logits, boxes)
+    R = boxes.size(0)
+    probs = torch.empty((R, C + 1), dtype=torch.float32, device=logits.device)
+    pred_boxes = torch.empty((R, 4 * C), dtype=torch.float32, device=logits.device)
+    check(_lib.load().soswsod_predict(_ptr(logits), logits.stride(0), col_ref0, ref_stride, _ptr(boxes.contiguous()), R, C,
+                                      K, *[float(x) for x in weights], _ptr(probs), _ptr(pred_boxes), _stream()), "predict")
+    return probs, pred_boxes
+
+
+def tta_accumulate(pred_boxes: torch.Tensor, probs: torch.Tensor, scale_x: float, scale_y: float, flipped: bool,
+                   view_w: float, first: bool, finalize_div: float, acc_boxes: torch.Tensor, acc_probs: torch.Tensor):
+    _need_cuda(pred_boxes, probs, acc_boxes, acc_probs)
+    R = probs.size(0)
+    C = probs.size(1) - 1
+    check(_lib.load().soswsod_tta_accumulate(_ptr(pred_boxes.contiguous()), _ptr(probs.contiguous()), R, C, float(scale_x),
+                                             float(scale_y), int(flipped), float(view_w), int(first), float(finalize_div),
+                                             _ptr(acc_boxes), _ptr(acc_probs), _stream()), "tta_accumulate")
+
+
+def nms(boxes: torch.Tensor, scores: torch.Tensor, iou_thr: float) -> torch.Tensor:
+    """torchvision.ops.nms drop-in: int64 indices of kept boxes, score-descending.  (One D2H read of the count.)"""
+    _need_cuda(boxes, scores)
+    n = boxes.size(0)
+    if n == 0:
+        return torch.empty((0,), dtype=torch.int64, device=boxes.device)
+    boxes = boxes.contiguous().float()
+    scores = scores.contiguous().float()
+    lib = _lib.load()
+    keep = torch.empty((n,), dtype=torch.int64, device=boxes.device)
+    num = torch.zeros((1,), dtype=torch.int32, device=boxes.device)
+    wsb = lib.soswsod_nms_workspace_bytes(n)
+    ws = torch.empty((wsb,), dtype=torch.uint8, device=boxes.device)
+    check(lib.soswsod_nms(_ptr(boxes), _ptr(scores), n, float(iou_thr), _ptr(keep), _ptr(num), _ptr(ws), wsb, _stream()),
+          "nms")
+    return keep[: int(num.item())]
+
+
+def detect(probs: torch.Tensor, pred_boxes: torch.Tensor, image_size: Tuple[float, float], score_thr: float,
+           nms_thr: float, topk: int, workspace: Optional[torch.Tensor] = None):
+    """fast_rcnn_inference_single_image on device.  Returns (det_boxes [topk,4], det_scores [topk], det_classes [topk],
+    det_rows [topk], num_det [1]) -- all device tensors, no host synchronisation."""
+    _need_cuda(probs, pred_boxes)
+    R, C1 = probs.shape
+    C = C1 - 1
+    dev = probs.device
+    lib = _lib.load()
+    wsb = lib.soswsod_detect_workspace_bytes(R, C)
+    if workspace is None or workspace.numel() < wsb:
+        workspace = torch.empty((wsb,), dtype=torch.uint8, device=dev)
+    db = torch.zeros((topk, 4), dtype=torch.float32, device=dev)
+    ds = torch.zeros((topk,), dtype=torch.float32, device=dev)
+    dc = torch.zeros((topk,), dtype=torch.int32, device=dev)
+    dr = torch.zeros((topk,), dtype=torch.int32, device=dev)
+    nd = torch.zeros((1,), dtype=torch.int32, device=dev)
+    check(lib.soswsod_detect(_ptr(probs.contiguous()), _ptr(pred_boxes.contiguous()), R, C, float(image_size[0]),
+                             float(image_size[1]), float(score_thr), float(nms_thr), int(topk), _ptr(db), _ptr(ds),
+                             _ptr(dc), _ptr(dr), _ptr(nd), _ptr(workspace), workspace.numel(), _stream()), "detect")
+    return db, ds, dc, dr, nd
