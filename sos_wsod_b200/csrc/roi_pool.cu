@@ -371,8 +371,9 @@ extern "C" int soswsod_roi_pool_forward(const float* feat, int n, int c, int h, 
                                         const float* row_scale, float row_scale_bias, float* out_f32,
                                         void* argmax, int argmax_dtype, void* out_bf16, long long ld_bf16,
                                         soswsod_stream_t stream) {
-    SOSWSOD_CHECK_ARG(feat && rois, "roi_pool_forward: null feat/rois");
     SOSWSOD_CHECK_ARG(n > 0 && c > 0 && h > 0 && w > 0 && num_rois >= 0, "roi_pool_forward: bad shape");
+    if (num_rois == 0) return SOSWSOD_OK;  // empty proposal list: nothing to write
+    SOSWSOD_CHECK_ARG(feat && rois, "roi_pool_forward: null feat/rois");
     SOSWSOD_CHECK_ARG(pooled_h > 0 && pooled_w > 0 && pooled_h * pooled_w <= kMaxBins,
                       "roi_pool_forward: pooled size %dx%d unsupported", pooled_h, pooled_w);
     SOSWSOD_CHECK_ARG(argmax_dtype == SOSWSOD_ARGMAX_I32 || argmax_dtype == SOSWSOD_ARGMAX_U16,
@@ -380,7 +381,6 @@ extern "C" int soswsod_roi_pool_forward(const float* feat, int n, int c, int h, 
     SOSWSOD_CHECK_ARG(argmax_dtype == SOSWSOD_ARGMAX_I32 || (long long)h * w < 65535,
                       "roi_pool_forward: uint16 argmax needs h*w < 65535");
     SOSWSOD_CHECK_ARG(!out_bf16 || ld_bf16 >= (long long)c * pooled_h * pooled_w, "roi_pool_forward: ld_bf16 too small");
-    if (num_rois == 0) return SOSWSOD_OK;
     cudaStream_t st = (cudaStream_t)stream;
     int32_t* a32 = argmax_dtype == SOSWSOD_ARGMAX_I32 ? (int32_t*)argmax : nullptr;
     uint16_t* a16 = argmax_dtype == SOSWSOD_ARGMAX_U16 ? (uint16_t*)argmax : nullptr;

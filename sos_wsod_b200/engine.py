@@ -1,0 +1,285 @@
+"""The fused OICR+ head step: all views of an image batched through ONE pass of
+ROI pool -> fc6 -> fc7 -> [cls | det | K x (cls_score, bbox_pred)] -> WSDDN -> K x OICR, with a hand-scheduled
+backward (no autograd graph) -- 23 kernel launches for a 4-view forward+backward instead of the reference's
+several thousand.
+
+What it follows in the reference (paths under uwsod/projects/WSL/wsl/modeling/roi_heads/):
+  train step   roi_heads_oicrplus.py:190-430 (_forward_box)   -- OICRPlusHeadEngine.train_step
+  test forward roi_heads_oicrplus.py:432-475 (_forward_box_test) + fast_rcnn_oicr.py:584-735 -- .test_forward
+Layout of the head logits matrix L [V*R, ld] fp32 (one GEMM for every output layer):
+  [0, C)            WSDDN classification stream   (box_predictor.cls)
+  [C, 2C)           WSDDN detection stream        (box_predictor.det)
+  2C + k*(5C+1) ..  branch k: C+1 class logits (box_refinery_k.cls_score) then 4C box deltas (.bbox_pred)
+  zero padding up to a multiple of 64 columns
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import ops
+
+
+@dataclass
+class HeadConfig:
+    num_classes: int = 20
+    refine_k: int = 3
+    pooled: int = 7
+    spatial_scale: float = 1.0 / 8
+    in_channels: int = 512
+    fc_dim: int = 4096
+    dropout_p: float = 0.5            # box_head.py:88-90 (training only)
+    mist_p: float = 0.10              # WSL.MIST_P
+    mist_thre: float = 0.05           # WSL.MIST_THRE
+    mist_nms: float = 0.01            # roi_heads_oicrplus.py:576-581
+    iou_thresholds: Tuple[float, float] = (0.5, 0.6)   # MODEL.ROI_HEADS.IOU_THRESHOLDS
+    bbox_reg_weights: Tuple[float, float, float, float] = (10.0, 10.0, 5.0, 5.0)
+    reproduce_flip_quirk: bool = True  # roi_heads_oicrplus.py:381
+    score_thresh_test: float = 1e-6
+    nms_thresh_test: float = 0.3
+    detections_per_image: int = 100
+
+    @property
+    def in_dim(self) -> int:
+        return self.in_channels * self.pooled * self.pooled
+
+    @property
+    def ref_stride(self) -> int:
+        return 5 * self.num_classes + 1
+
+    @property
+    def col_ref0(self) -> int:
+        return 2 * self.num_classes
+
+    @property
+    def head_cols(self) -> int:
+        return 2 * self.num_classes + self.refine_k * self.ref_stride
+
+    @property
+    def head_cols_padded(self) -> int:
+        return (self.head_cols + 63) // 64 * 64
+
+    def top_k(self, R: int) -> int:
+        # roi_heads_oicrplus.py:657-662 (Python float arithmetic, then int())
+        p = self.mist_p
+        if p >= 1:
+            return min(R, int(p))
+        if 0 < p < 1:
+            return max(int(R * p), 1)
+        return min(R, 1)
+
+
+class HeadOperands:
+    """bf16 GEMM-operand copies of the fp32 master parameters (names = the reference's checkpoint keys:
+    box_head.fc1/fc2, box_predictor.cls/det, box_refinery_k.cls_score/bbox_pred)."""
+
+    def __init__(self, cfg: HeadConfig, fc1_w, fc1_b, fc2_w, fc2_b, cls_w, cls_b, det_w, det_b, refine):
+        self.cfg = cfg
+        self.master = {"fc1_w": fc1_w, "fc1_b": fc1_b, "fc2_w": fc2_w, "fc2_b": fc2_b, "cls_w": cls_w, "cls_b": cls_b,
+                       "det_w": det_w, "det_b": det_b}
+        for k, (cw, cb, bw, bb) in enumerate(refine):
+            self.master.update({f"r{k}_cls_w": cw, f"r{k}_cls_b": cb, f"r{k}_box_w": bw, f"r{k}_box_b": bb})
+        dev = fc1_w.device
+        self.w6 = torch.empty(fc1_w.shape, dtype=torch.bfloat16, device=dev)
+        self.w7 = torch.empty(fc2_w.shape, dtype=torch.bfloat16, device=dev)
+        self.wh = torch.zeros((cfg.head_cols_padded, cfg.fc_dim), dtype=torch.bfloat16, device=dev)
+        self.bh = torch.zeros((cfg.head_cols_padded,), dtype=torch.float32, device=dev)
+        self._versions = None
+        self.refresh()
+
+    def head_slices(self) -> List[Tuple[str, str, int, int]]:
+        """(weight key, bias key, first row, number of rows) of every output layer inside the fused head matrix."""
+        C, K = self.cfg.num_classes, self.cfg.refine_k
+        out = [("cls_w", "cls_b", 0, C), ("det_w", "det_b", C, C)]
+        for k in range(K):
+            c0 = self.cfg.col_ref0 + k * self.cfg.ref_stride
+            out.append((f"r{k}_cls_w", f"r{k}_cls_b", c0, C + 1))
+            out.append((f"r{k}_box_w", f"r{k}_box_b", c0 + C + 1, 4 * C))
+        return out
+
+    def _current_versions(self):
+        return tuple(t._version for t in self.master.values())
+
+    def refresh(self, force: bool = True) -> None:
+        """Re-casts the operands if any master parameter changed (optimizer step, checkpoint load)."""
+        v = self._current_versions()
+        if not force and v == self._versions:
+            return
+        m = self.master
+        with torch.no_grad():
+            ops.cast_f32_bf16(m["fc1_w"].detach(), out=self.w6)
+            ops.cast_f32_bf16(m["fc2_w"].detach(), out=self.w7)
+            for wk, bk, r0, n in self.head_slices():
+                ops.cast_f32_bf16(m[wk].detach(), out=self.wh[r0:r0 + n])
+                self.bh[r0:r0 + n].copy_(m[bk].detach())
+        self._versions = self._current_versions()
+
+
+@dataclass
+class ViewBatch:
+    """Inputs of one head step.  `feats[i]` is an NCHW fp32 conv5 map holding n_i views (the reference batches an
+    image with its flip, rcnn_multi.py:174-175); `rois[i]` is [n_i*R, 5] = (index inside feats[i], x1, y1, x2, y2)
+    ordered view-major; `obj` is [V*R] objectness logits in the same global row order.  V = sum n_i."""
+    feats: List[torch.Tensor]
+    rois: List[torch.Tensor]
+    obj: torch.Tensor
+    R: int
+
+    @property
+    def num_views(self) -> int:
+        return sum(int(f.size(0)) for f in self.feats)
+
+    def view_boxes(self) -> torch.Tensor:
+        """[V, R, 4] proposal boxes per view."""
+        return torch.cat([r[:, 1:5] for r in self.rois], 0).reshape(self.num_views, self.R, 4).contiguous()
+
+
+@dataclass
+class TrainOutput:
+    losses: Dict[str, torch.Tensor]
+    grads: Dict[str, torch.Tensor]          # keyed like HeadOperands.master
+    grad_feats: List[torch.Tensor]          # d loss / d feats[i]
+    aux: Dict[str, torch.Tensor] = field(default_factory=dict)
+
+
+class OICRPlusHeadEngine:
+    def __init__(self, cfg: HeadConfig, operands: HeadOperands):
+        self.cfg = cfg
+        self.op = operands
+        self.launches_last_step = 0
+
+    # -------------------------------------------------------------------------------------------
+    def _pool(self, vb: ViewBatch, keep_argmax: bool):
+        cfg = self.cfg
+        V, R = vb.num_views, vb.R
+        X = torch.empty((V * R, cfg.in_dim), dtype=torch.bfloat16, device=vb.obj.device)
+        argmaxes = []
+        row = 0
+        for f, r in zip(vb.feats, vb.rois):
+            m = r.size(0)
+            u16 = f.size(2) * f.size(3) < 65535
+            _, am, _ = ops.roi_pool_forward(f, r, (cfg.pooled, cfg.pooled), cfg.spatial_scale,
+                                            row_scale=vb.obj[row:row + m], row_scale_bias=1.0, want_f32=False,
+                                            argmax_u16=u16, out_bf16=X[row:row + m])
+            argmaxes.append(am if keep_argmax else None)
+            row += m
+            self.launches_last_step += 1
+        return X, argmaxes
+
+    def _trunk(self, X, train: bool, seeds: Tuple[int, int]):
+        cfg, op = self.cfg, self.op
+        p = cfg.dropout_p if train else 0.0
+        H6 = ops.gemm_bf16(X, op.w6, out_dtype=torch.bfloat16, bias=op.master["fc1_b"].detach(), relu=True, dropout_p=p,
+                           dropout_seed=seeds[0])
+        H7 = ops.gemm_bf16(H6, op.w7, out_dtype=torch.bfloat16, bias=op.master["fc2_b"].detach(), relu=True, dropout_p=p,
+                           dropout_seed=seeds[1])
+        L = ops.gemm_bf16(H7, op.wh, out_dtype=torch.float32, bias=op.bh)
+        self.launches_last_step += 3
+        return H6, H7, L
+
+    # -------------------------------------------------------------------------------------------
+    def train_step(self, vb: ViewBatch, gt_classes_img: torch.Tensor, dropout_seeds: Tuple[int, int] = (1, 2),
+                   need_feat_grad: bool = True, loss_scale: float = 1.0) -> TrainOutput:
+        """Forward + backward of the head for one image (V views).  gt_classes_img: int [G] sorted ascending
+        (get_image_level_gt, roi_heads.py:144-164).  Gradients are those of loss_scale * sum(all loss keys)."""
+        cfg, op = self.cfg, self.op
+        op.refresh(force=False)
+        self.launches_last_step = 0
+        C, K, V, R = cfg.num_classes, cfg.refine_k, vb.num_views, vb.R
+        dev = vb.obj.device
+        gt_int = gt_classes_img.to(device=dev, dtype=torch.int32)
+        gt_oh = torch.zeros((C,), dtype=torch.float32, device=dev)
+        gt_oh[gt_int.long()] = 1.0
+        boxes = vb.view_boxes()
+
+        # ---------------- forward ----------------
+        X, argmaxes = self._pool(vb, keep_argmax=need_feat_grad)
+        H6, H7, L = self._trunk(X, True, dropout_seeds)
+        ldp = cfg.head_cols_padded
+        dL = torch.zeros((V * R, ldp), dtype=torch.float32, device=dev)
+        scores, img_scores, wloss = ops.wsddn_forward(L, 0, C, V, R, C, gt_oh, dlogits=dL)
+        prev = ops.oicr_avg_scores(scores, L, cfg.col_ref0, cfg.ref_stride, V, R, C, K)
+        mined = ops.oicr_mine_label(prev, boxes[0], gt_int, C, cfg.top_k(R), cfg.mist_thre, cfg.mist_nms,
+                                    cfg.iou_thresholds[0], cfg.iou_thresholds[1])
+        olosses, view_losses, acc = ops.oicr_loss(L, cfg.col_ref0, cfg.ref_stride, boxes, mined["gt_class"],
+                                                  mined["gt_weight"], mined["gt_index"], V, R, C, K,
+                                                  flip_quirk=cfg.reproduce_flip_quirk and V == 4,
+                                                  weights=cfg.bbox_reg_weights, dlogits=dL)
+        self.launches_last_step += 6
+        losses = {"loss_cls": wloss.mean()}                       # roi_heads_oicrplus.py:283-288
+        for k in range(K):
+            losses[f"loss_cls_r{k}"] = olosses[k, 0]
+            losses[f"loss_box_reg_r{k}"] = olosses[k, 1]
+
+        # ---------------- backward ----------------
+        # wsddn_forward wrote d loss_v / d logits; loss_cls is the mean over views -> scale its two blocks by 1/V
+        col_scale = torch.full((ldp,), float(loss_scale), dtype=torch.float32, device=dev)
+        col_scale[:2 * C] = float(loss_scale) / V
+        dLb, _ = ops.cast_f32_bf16(dL, col_scale=col_scale)
+        mscale = 1.0 / (1.0 - cfg.dropout_p) if cfg.dropout_p > 0 else 1.0
+        dWh = ops.gemm_bf16(dLb, H7, a_mn=True, b_mn=True)                                          # [ldp, fc]
+        dbh = ops.colsum(dL) * col_scale
+        dH7 = ops.gemm_bf16(dLb, op.wh, b_mn=True, out_dtype=torch.bfloat16, mask_src=H7, mask_scale=mscale)
+        dW7 = ops.gemm_bf16(dH7, H6, a_mn=True, b_mn=True)
+        db7 = ops.colsum(dH7)
+        dH6 = ops.gemm_bf16(dH7, op.w7, b_mn=True, out_dtype=torch.bfloat16, mask_src=H6, mask_scale=mscale)
+        dW6 = ops.gemm_bf16(dH6, X, a_mn=True, b_mn=True)
+        db6 = ops.colsum(dH6)
+        self.launches_last_step += 9
+        grad_feats: List[torch.Tensor] = []
+        if need_feat_grad:
+            dX = ops.gemm_bf16(dH6, op.w6, b_mn=True, out_dtype=torch.bfloat16)
+            self.launches_last_step += 1
+            row = 0
+            for f, r, am in zip(vb.feats, vb.rois, argmaxes):
+                m = r.size(0)
+                grad_feats.append(ops.roi_pool_backward(dX[row:row + m], am, r, tuple(f.shape), (cfg.pooled, cfg.pooled),
+                                                        row_scale=vb.obj[row:row + m], row_scale_bias=1.0))
+                row += m
+                self.launches_last_step += 1
+        grads = {"fc1_w": dW6, "fc1_b": db6, "fc2_w": dW7, "fc2_b": db7}
+        for wk, bk, r0, n in op.head_slices():
+            grads[wk] = dWh[r0:r0 + n]
+            grads[bk] = dbh[r0:r0 + n]
+        aux = {"scores": scores, "img_scores": img_scores, "prev": prev, "logits": L, "x": H7, "acc_counts": acc,
+               "view_losses": view_losses, "wsddn_view_losses": wloss}
+        aux.update(mined)
+        return TrainOutput(losses=losses, grads=grads, grad_feats=grad_feats, aux=aux)
+
+    # -------------------------------------------------------------------------------------------
+    def test_forward(self, vb: ViewBatch):
+        """_forward_box_test for V views at once -> (probs [V,R,C+1], pred_boxes [V,R,4C]) in each view's own
+        coordinates (predict_probs_K / predict_boxes_K, fast_rcnn_oicr.py:674-735)."""
+        cfg, op = self.cfg, self.op
+        op.refresh(force=False)
+        self.launches_last_step = 0
+        C, K, V, R = cfg.num_classes, cfg.refine_k, vb.num_views, vb.R
+        X, _ = self._pool(vb, keep_argmax=False)
+        _, _, L = self._trunk(X, False, (0, 0))
+        boxes = vb.view_boxes().reshape(V * R, 4)
+        probs, pred_boxes = ops.predict(L, cfg.col_ref0, cfg.ref_stride, boxes, C, K, cfg.bbox_reg_weights)
+        self.launches_last_step += 1
+        return probs.view(V, R, C + 1), pred_boxes.view(V, R, 4 * C)
+
+    def detect(self, probs: torch.Tensor, pred_boxes: torch.Tensor, image_size: Tuple[int, int], workspace=None):
+        """fast_rcnn_inference_single_image (fast_rcnn_oicr.py:86-148) on device."""
+        cfg = self.cfg
+        self.launches_last_step += 5
+        return ops.detect(probs, pred_boxes, image_size, cfg.score_thresh_test, cfg.nms_thresh_test,
+                          cfg.detections_per_image, workspace)
+
+    def tta_detect(self, vb: ViewBatch, view_tfms: Sequence[Tuple[float, float, bool, float]], image_size: Tuple[int, int]):
+        """GeneralizedRCNNWithTTAAVG._get_augmented_boxes + _merge_detections
+        (test_time_augmentation_avg.py:349-387): per-view inference, inverse transform, mean over views, one NMS.
+        view_tfms[v] = (scale_x, scale_y, flipped, view_width) mapping view v back to the original image."""
+        cfg = self.cfg
+        probs, pboxes = self.test_forward(vb)
+        V, R, C = vb.num_views, vb.R, cfg.num_classes
+        acc_b = torch.empty((R, 4 * C), dtype=torch.float32, device=probs.device)
+        acc_p = torch.empty((R, C + 1), dtype=torch.float32, device=probs.device)
+        for v, (sx, sy, fl, vw) in enumerate(view_tfms):
+            ops.tta_accumulate(pboxes[v], probs[v], sx, sy, fl, vw, v == 0, float(V) if v == V - 1 else 0.0, acc_b, acc_p)
+            self.launches_last_step += 1
+        return self.detect(acc_p, acc_b, image_size), acc_p, acc_b
