@@ -149,6 +149,8 @@ class OICRPlusHeadEngine:
         self.cfg = cfg
         self.op = operands
         self.launches_last_step = 0
+        self.grad_hook = None
+        self.last_output: Optional[TrainOutput] = None
 
     # -------------------------------------------------------------------------------------------
     def _pool(self, vb: ViewBatch, keep_argmax: bool):
@@ -181,9 +183,12 @@ class OICRPlusHeadEngine:
 
     # -------------------------------------------------------------------------------------------
     def train_step(self, vb: ViewBatch, gt_classes_img: torch.Tensor, dropout_seeds: Tuple[int, int] = (1, 2),
-                   need_feat_grad: bool = True, loss_scale: float = 1.0) -> TrainOutput:
+                   need_feat_grad: bool = True, loss_scale: float = 1.0, grad_hook=None) -> TrainOutput:
         """Forward + backward of the head for one image (V views).  gt_classes_img: int [G] sorted ascending
-        (get_image_level_gt, roi_heads.py:144-164).  Gradients are those of loss_scale * sum(all loss keys)."""
+        (get_image_level_gt, roi_heads.py:144-164).  Gradients are those of loss_scale * sum(all loss keys).
+        grad_hook(name, [tensors]) is called as soon as the kernels producing a layer's parameter gradients are
+        queued -- the data-parallel caller starts that layer's NCCL all-reduce there, so it overlaps the remaining
+        backward kernels (the reference gets the same overlap from DDP buckets, tools/train_net_multi.py:75-78)."""
         cfg, op = self.cfg, self.op
         op.refresh(force=False)
         self.launches_last_step = 0
@@ -221,12 +226,18 @@ class OICRPlusHeadEngine:
         mscale = 1.0 / (1.0 - cfg.dropout_p) if cfg.dropout_p > 0 else 1.0
         dWh = ops.gemm_bf16(dLb, H7, a_mn=True, b_mn=True)                                          # [ldp, fc]
         dbh = ops.colsum(dL) * col_scale
+        if grad_hook is not None:
+            grad_hook("head", [dWh, dbh])
         dH7 = ops.gemm_bf16(dLb, op.wh, b_mn=True, out_dtype=torch.bfloat16, mask_src=H7, mask_scale=mscale)
         dW7 = ops.gemm_bf16(dH7, H6, a_mn=True, b_mn=True)
         db7 = ops.colsum(dH7)
+        if grad_hook is not None:
+            grad_hook("fc2", [dW7, db7])
         dH6 = ops.gemm_bf16(dH7, op.w7, b_mn=True, out_dtype=torch.bfloat16, mask_src=H6, mask_scale=mscale)
         dW6 = ops.gemm_bf16(dH6, X, a_mn=True, b_mn=True)
         db6 = ops.colsum(dH6)
+        if grad_hook is not None:
+            grad_hook("fc1", [dW6, db6])
         self.launches_last_step += 9
         grad_feats: List[torch.Tensor] = []
         if need_feat_grad:

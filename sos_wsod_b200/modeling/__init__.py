@@ -1,0 +1,8 @@
+from .box_head import DiscriminativeAdaptionNeck, build_box_head
+from .fast_rcnn_oicr import OICROutputLayers
+from .fast_rcnn_wsddn import WSDDNOutputLayers
+from .poolers import ROIPooler, convert_boxes_to_pooler_format
+from .roi_heads_oicrplus import OICRPlusHeads, build_roi_heads, get_image_level_gt
+
+__all__ = ["ROIPooler", "convert_boxes_to_pooler_format", "DiscriminativeAdaptionNeck", "build_box_head",
+           "WSDDNOutputLayers", "OICROutputLayers", "OICRPlusHeads", "build_roi_heads", "get_image_level_gt"]

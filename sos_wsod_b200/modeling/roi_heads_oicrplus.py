@@ -1,0 +1,225 @@
+"""OICRPlusHeads -- the reference's Stage-1 ROI head (uwsod/projects/WSL/wsl/modeling/roi_heads/
+roi_heads_oicrplus.py:36-757) as a drop-in: same registry name, constructor kwargs, sub-module and parameter
+names (box_pooler, box_head.fc1/fc2, box_predictor.cls/det, box_refinery_{k}.cls_score/bbox_pred), same
+forward signature and return structure.  Training and inference both run through the fused engine
+(engine.py): all views batched through one ROI-pool/fc6/fc7/head pass with a hand-scheduled backward."""
+from __future__ import annotations
+
+from typing import Dict, List, Optional
+
+import torch
+from torch import nn
+from torch.autograd import Function
+from torch.autograd.function import once_differentiable
+
+from ..engine import HeadConfig, HeadOperands, OICRPlusHeadEngine, ViewBatch
+from ..registry import ROI_HEADS_REGISTRY
+from ..structures import Boxes, ImageList, Instances, ShapeSpec
+from .box_head import build_box_head
+from .fast_rcnn_oicr import OICROutputLayers, _detections_to_instances
+from .fast_rcnn_wsddn import WSDDNOutputLayers
+from .poolers import ROIPooler
+
+
+def get_image_level_gt(targets: List[Instances], num_classes: int):
+    """uwsod/projects/WSL/wsl/modeling/roi_heads/roi_heads.py:144-164 -> (list of per-image class tensors,
+    unique sorted int64 classes per image, one-hot [N_img, C])."""
+    if targets is None:
+        return None, None, None
+    gt_classes_img = [torch.unique(t.gt_classes, sorted=True) for t in targets]
+    gt_classes_img_int = [gt.to(torch.int64) for gt in gt_classes_img]
+    gt_classes_img_oh = torch.cat(
+        [torch.zeros((1, num_classes), dtype=torch.float, device=gt.device).scatter_(1, torch.unsqueeze(gt, dim=0), 1)
+         for gt in gt_classes_img_int], dim=0)
+    return gt_classes_img, gt_classes_img_int, gt_classes_img_oh
+
+
+class _FusedHeadStep(Function):
+    """Runs engine.train_step in forward (which already produces every gradient of sum(losses)) and hands the
+    stored gradients to autograd in backward.  Inputs: feats..., then the parameters in HeadOperands.master order."""
+
+    @staticmethod
+    def forward(ctx, engine, vb, gt_int, seeds, n_feats, *tensors):
+        feats = tensors[:n_feats]
+        need_fg = any(f.requires_grad for f in feats)
+        out = engine.train_step(ViewBatch([f.detach() for f in feats], vb.rois, vb.obj, vb.R), gt_int, seeds,
+                                need_feat_grad=need_fg, grad_hook=engine.grad_hook)
+        ctx.engine_out = out
+        ctx.n_feats = n_feats
+        ctx.keys = list(engine.op.master.keys())
+        ctx.loss_keys = list(out.losses.keys())
+        engine.last_output = out
+        return tuple(out.losses[k].clone() for k in ctx.loss_keys)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, *gouts):
+        out = ctx.engine_out
+        g = torch.stack([x.reshape(()) for x in gouts]).tolist()     # one tiny D2H read
+        if any(abs(v - g[0]) > 1e-12 * max(1.0, abs(g[0])) for v in g):
+            raise NotImplementedError(
+                "the fused OICR+ head step produces the gradient of s * sum(loss_dict.values()) -- the reference "
+                "trainer's objective (tools/train_net_multi.py:139); per-key loss weights are not supported")
+        s = g[0]
+        def sc(t):
+            return t if s == 1.0 else t * s
+        gf = [sc(t) for t in out.grad_feats] if out.grad_feats else [None] * ctx.n_feats
+        gp = [sc(out.grads[k]) for k in ctx.keys]
+        ctx.engine_out = None
+        return (None, None, None, None, None, *gf, *gp)
+
+
+@ROI_HEADS_REGISTRY.register()
+class OICRPlusHeads(nn.Module):
+    def __init__(self, *, box_in_features: List[str], box_pooler: ROIPooler, box_head: nn.Module,
+                 box_predictor: nn.Module, vis_period: int = 0, refine_K: int = 4, refine_mist: bool = False,
+                 mist_p: float = 0.10, mist_thre: float = 0.05, mist_type: str = "nms",
+                 refine_reg: List[bool] = (False, False, False, False), box_refinery: List[nn.Module] = (None,) * 4,
+                 cls_agnostic_bbox_reg: bool = False, pooler_type: str = "ROIPool", cfg=None, num_classes: int = 20,
+                 **kwargs):
+        super().__init__()
+        assert mist_type in ["nms", "wetectron"], f"{mist_type} is wrong"
+        if mist_type != "nms" or not refine_mist:
+            raise NotImplementedError("only REFINE_MIST: True with MIST_TYPE: nms (the released OICR+ configuration) is "
+                                      "built; the reference's 'wetectron' variant references an undefined attribute "
+                                      "(roi_heads_oicrplus.py:555) and cannot run there either")
+        assert pooler_type == "ROIPool"
+        self.mist_type, self.mist_p, self.mist_thre = mist_type, mist_p, mist_thre
+        self.cfg = cfg
+        self.num_classes = num_classes
+        self.in_features = self.box_in_features = box_in_features
+        self.box_pooler = box_pooler
+        self.box_head = box_head
+        self.box_predictor = box_predictor
+        self.pooler_type = pooler_type
+        self.iter = 0
+        self.iter_test = 0
+        self.vis_period = vis_period
+        self.refine_K = refine_K
+        self.refine_mist = refine_mist
+        self.refine_reg = list(refine_reg)
+        self.box_refinery = list(box_refinery)
+        for k in range(self.refine_K):
+            self.add_module("box_refinery_{}".format(k), self.box_refinery[k])
+        self.cls_agnostic_bbox_reg = cls_agnostic_bbox_reg
+        self.reproduce_flip_quirk = True     # roi_heads_oicrplus.py:381; set False to use the flipped logits
+        self._engine: Optional[OICRPlusHeadEngine] = None
+        # data-parallel callers set this to start a layer's gradient all-reduce as soon as it is produced
+        self.grad_hook = None
+        self.last_metrics: Dict[str, torch.Tensor] = {}
+
+    # ---- construction from config (roi_heads_oicrplus.py:88-147) ----
+    @classmethod
+    def from_config(cls, cfg, input_shape: Dict[str, ShapeSpec]):
+        in_features = cfg.MODEL.ROI_HEADS.IN_FEATURES
+        res = cfg.MODEL.ROI_BOX_HEAD.POOLER_RESOLUTION
+        scale = 1.0 / input_shape[in_features[-1]].stride
+        in_channels = input_shape[in_features[-1]].channels
+        box_pooler = ROIPooler(output_size=res, scales=(scale,), sampling_ratio=cfg.MODEL.ROI_BOX_HEAD.POOLER_SAMPLING_RATIO,
+                               pooler_type=cfg.MODEL.ROI_BOX_HEAD.POOLER_TYPE)
+        box_head = build_box_head(cfg, ShapeSpec(channels=in_channels, height=res, width=res))
+        box_predictor = WSDDNOutputLayers(cfg, box_head.output_shape)
+        K = cfg.WSL.REFINE_NUM
+        return cls(box_in_features=in_features, box_pooler=box_pooler, box_head=box_head, box_predictor=box_predictor,
+                   vis_period=cfg.VIS_PERIOD, refine_K=K, refine_mist=cfg.WSL.REFINE_MIST, mist_p=cfg.WSL.MIST_P,
+                   mist_thre=cfg.WSL.MIST_THRE, mist_type=cfg.WSL.MIST_TYPE, refine_reg=cfg.WSL.REFINE_REG,
+                   box_refinery=[OICROutputLayers(cfg, box_head.output_shape, k) for k in range(K)],
+                   cls_agnostic_bbox_reg=cfg.MODEL.ROI_BOX_HEAD.CLS_AGNOSTIC_BBOX_REG,
+                   pooler_type=cfg.MODEL.ROI_BOX_HEAD.POOLER_TYPE, cfg=cfg, num_classes=cfg.MODEL.ROI_HEADS.NUM_CLASSES)
+
+    # ---- engine plumbing ----
+    def head_config(self) -> HeadConfig:
+        cfg = self.cfg
+        fc1 = self.box_head.fc1
+        res = self.box_pooler.output_size[0]
+        hc = HeadConfig(num_classes=self.num_classes, refine_k=self.refine_K, pooled=res,
+                        spatial_scale=self.box_pooler.level_poolers[0].spatial_scale,
+                        in_channels=fc1.in_features // (res * res), fc_dim=fc1.out_features,
+                        dropout_p=self.box_head.dropout, mist_p=self.mist_p, mist_thre=self.mist_thre,
+                        reproduce_flip_quirk=self.reproduce_flip_quirk)
+        if cfg is not None:
+            hc.iou_thresholds = tuple(cfg.MODEL.ROI_HEADS.IOU_THRESHOLDS)
+            hc.bbox_reg_weights = tuple(cfg.MODEL.ROI_BOX_HEAD.BBOX_REG_WEIGHTS)
+            hc.score_thresh_test = cfg.MODEL.ROI_HEADS.SCORE_THRESH_TEST
+            hc.nms_thresh_test = cfg.MODEL.ROI_HEADS.NMS_THRESH_TEST
+            hc.detections_per_image = cfg.TEST.DETECTIONS_PER_IMAGE
+        return hc
+
+    def engine(self) -> OICRPlusHeadEngine:
+        dev = self.box_head.fc1.weight.device
+        if self._engine is None or self._engine.op.w6.device != dev:
+            hc = self.head_config()
+            bh, bp = self.box_head, self.box_predictor
+            refine = [(r.cls_score.weight, r.cls_score.bias, r.bbox_pred.weight, r.bbox_pred.bias)
+                      for r in self.box_refinery[:self.refine_K]]
+            op = HeadOperands(hc, bh.fc1.weight, bh.fc1.bias, bh.fc2.weight, bh.fc2.bias, bp.cls.weight, bp.cls.bias,
+                              bp.det.weight, bp.det.bias, refine)
+            self._engine = OICRPlusHeadEngine(hc, op)
+        self._engine.cfg.reproduce_flip_quirk = self.reproduce_flip_quirk
+        self._engine.grad_hook = self.grad_hook
+        return self._engine
+
+    def _param_list(self):
+        return list(self.engine().op.master.values())
+
+    @staticmethod
+    def _view_rois(proposal_groups: List[List[Instances]]):
+        """One roi tensor per feature tensor: views of a group are the batch entries 0..n-1 of that tensor."""
+        rois, obj = [], []
+        for group in proposal_groups:
+            parts = []
+            for i, p in enumerate(group):
+                t = p.proposal_boxes.tensor
+                parts.append(torch.cat((torch.full((len(t), 1), float(i), dtype=t.dtype, device=t.device), t), 1))
+                obj.append(p.objectness_logits)
+            rois.append(torch.cat(parts, 0).contiguous())
+        return rois, torch.cat(obj, 0).float().contiguous()
+
+    # ---- forward (roi_heads_oicrplus.py:149-188) ----
+    def forward(self, images_list, features_list, proposals_list, targets_list=(None, None, None, None)):
+        if not self.training:
+            pred_instances, all_scores, all_boxes = self._forward_box_test(features_list, proposals_list, targets_list)
+            return pred_instances, {}, all_scores, all_boxes
+        features1, features2 = features_list
+        proposals1, proposals1_flip, proposals2, proposals2_flip = proposals_list
+        targets1 = targets_list[0]
+        self.gt_classes_img, self.gt_classes_img_int, self.gt_classes_img_oh = get_image_level_gt(targets1, self.num_classes)
+        f1 = features1[self.box_in_features[-1]]
+        f2 = features2[self.box_in_features[-1]]
+        losses = self._forward_box(f1, f2, proposals1, proposals1_flip, proposals2, proposals2_flip)
+        self.iter = self.iter + 1
+        return None, losses
+
+    def _forward_box(self, features1, features2, proposals1, proposals1_flip, proposals2, proposals2_flip):
+        """features1/2: [2,C,h,w] (image, flipped image) of the two scales; one image per GPU (rcnn_multi.py:148)."""
+        assert len(proposals1) == 1, "the reference trains with one image per GPU (rcnn_multi.py:148)"
+        eng = self.engine()
+        rois, obj = self._view_rois([[proposals1[0], proposals1_flip[0]], [proposals2[0], proposals2_flip[0]]])
+        R = len(proposals1[0])
+        vb = ViewBatch([features1, features2], rois, obj, R)
+        seeds = (torch.initial_seed() * 7919 + 2 * self.iter + 1, torch.initial_seed() * 7919 + 2 * self.iter + 2)
+        outs = _FusedHeadStep.apply(eng, vb, self.gt_classes_img_int[0], seeds, 2, features1, features2, *self._param_list())
+        out = eng.last_output
+        self.last_metrics = {"acc_counts": out.aux["acc_counts"], "label_counts": out.aux["counts"]}
+        return dict(zip(out.losses.keys(), outs))
+
+    def _forward_box_test(self, features, proposals, targets=None):
+        """roi_heads_oicrplus.py:432-475: single view -> ([Instances], all_scores [1,R,C+1], all_boxes [1,R,4C])."""
+        eng = self.engine()
+        if isinstance(features, dict):
+            f = features[self.box_in_features[-1]]
+        else:
+            f = features[0] if isinstance(features, (list, tuple)) else features
+            if isinstance(f, dict):
+                f = f[self.box_in_features[-1]]
+        assert len(proposals) == 1 and f.size(0) == 1, "inference runs one image (view) per call, as the reference's TTA does"
+        rois, obj = self._view_rois([[proposals[0]]])
+        vb = ViewBatch([f], rois, obj, len(proposals[0]))
+        probs, pboxes = eng.test_forward(vb)
+        inst, _ = _detections_to_instances(eng.detect(probs[0], pboxes[0], proposals[0].image_size), proposals[0].image_size)
+        return inst, probs, pboxes
+
+
+def build_roi_heads(cfg, input_shape):
+    """uwsod/detectron2/modeling/roi_heads/roi_heads.py:38-43."""
+    return ROI_HEADS_REGISTRY.get(cfg.MODEL.ROI_HEADS.NAME).from_config(cfg, input_shape)

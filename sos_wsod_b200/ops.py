@@ -11,6 +11,14 @@ from . import _lib
 from ._lib import ARGMAX_I32, ARGMAX_U16, DTYPE_BF16, DTYPE_F32, check
 
 
+# Number of kernels of THIS library launched so far (bench.py reports the delta over its timed region).
+COUNTERS = {"launches": 0}
+
+
+def _count(n: int) -> None:
+    COUNTERS["launches"] += n
+
+
 def _ptr(t: Optional[torch.Tensor]):
     return None if t is None else t.data_ptr()
 
@@ -67,6 +75,7 @@ def roi_pool_forward(feat: torch.Tensor, rois: torch.Tensor, pooled: Tuple[int, 
                                        _ptr(row_scale), float(row_scale_bias), _ptr(out), _ptr(argmax),
                                        ARGMAX_U16 if argmax_u16 else ARGMAX_I32, _ptr(obf), ld, _stream()),
           "roi_pool_forward")
+    _count(1)
     return out, argmax, obf
 
 
@@ -93,6 +102,7 @@ def roi_pool_backward(grad_out: torch.Tensor, argmax: torch.Tensor, rois: torch.
     check(lib.soswsod_roi_pool_backward(_ptr(grad_out), _dt(grad_out), grad_out.stride(0), _ptr(argmax.contiguous()), a_dt,
                                         _ptr(rois), m, _ptr(row_scale), float(row_scale_bias), n, c, h, w, ph, pw,
                                         _ptr(grad_feat), _stream()), "roi_pool_backward")
+    _count(1)
     return grad_feat
 
 
@@ -131,6 +141,7 @@ def gemm_bf16(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: boo
                                 out.stride(0), _dt(out), m, n, k, _ptr(bias), int(relu), _ptr(mask_src), ld_mask,
                                 float(mask_scale), float(dropout_p), int(dropout_seed) & 0xFFFFFFFFFFFFFFFF, _stream()),
           "gemm_bf16")
+    _count(1)
     return out
 
 
@@ -138,6 +149,7 @@ def dropout_mask(m: int, n: int, p: float, seed: int, device="cuda") -> torch.Te
     mask = torch.empty((m, n), dtype=torch.uint8, device=device)
     check(_lib.load().soswsod_dropout_mask(_ptr(mask), m, n, float(p), int(seed) & 0xFFFFFFFFFFFFFFFF, _stream()),
           "dropout_mask")
+    _count(1)
     return mask
 
 
@@ -159,6 +171,7 @@ def cast_f32_bf16(x: torch.Tensor, col_scale: Optional[torch.Tensor] = None, wan
     check(_lib.load().soswsod_cast_f32_bf16(_ptr(x), x.stride(0), rows, cols, _ptr(col_scale), _ptr(o),
                                             0 if o is None else o.stride(0), _ptr(ot), 0 if ot is None else ot.stride(0),
                                             _stream()), "cast_f32_bf16")
+    _count(1)
     return o, ot
 
 
@@ -170,6 +183,7 @@ def transpose_bf16(x: torch.Tensor, ld_pad: int = 8) -> torch.Tensor:
     ot = torch.zeros((cols, rp), dtype=torch.bfloat16, device=x.device)[:, :rows]
     check(_lib.load().soswsod_transpose_bf16(_ptr(x), x.stride(0), rows, cols, _ptr(ot), ot.stride(0), _stream()),
           "transpose_bf16")
+    _count(1)
     return ot
 
 
@@ -180,6 +194,7 @@ def colsum(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     if out is None:
         out = torch.empty((cols,), dtype=torch.float32, device=x.device)
     check(_lib.load().soswsod_colsum(_ptr(x), _dt(x), x.stride(0), rows, cols, _ptr(out), _stream()), "colsum")
+    _count(1)
     return out
 
 
@@ -191,6 +206,7 @@ def sgd_step(param: torch.Tensor, grad: torch.Tensor, buf: torch.Tensor, lr: flo
     assert param_bf16 is None or (param_bf16.is_contiguous() and param_bf16.dtype == torch.bfloat16)
     check(_lib.load().soswsod_sgd_step(_ptr(param), _ptr(grad), _ptr(buf), param.numel(), float(lr), float(momentum),
                                        float(weight_decay), float(grad_scale), _ptr(param_bf16), _stream()), "sgd_step")
+    _count(1)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -211,6 +227,7 @@ def wsddn_forward(logits: torch.Tensor, col_cls: int, col_det: int, num_views: i
     check(_lib.load().soswsod_wsddn_forward(_ptr(logits), logits.stride(0), col_cls, col_det, num_views, R, C, _ptr(gt),
                                             _ptr(scores), _ptr(img), _ptr(loss), _ptr(dlogits),
                                             0 if dlogits is None else dlogits.stride(0), _stream()), "wsddn_forward")
+    _count(1)
     return scores, img, loss
 
 
@@ -224,6 +241,7 @@ def oicr_avg_scores(wsddn_scores: torch.Tensor, logits: Optional[torch.Tensor], 
     check(_lib.load().soswsod_oicr_avg_scores(_ptr(wsddn_scores.contiguous()), _ptr(logits),
                                               0 if logits is None else logits.stride(0), col_ref0, ref_stride,
                                               num_views, R, C, K, _ptr(prev), _stream()), "oicr_avg_scores")
+    _count(1)
     return prev
 
 
@@ -256,6 +274,7 @@ def oicr_mine_label(prev: torch.Tensor, boxes: torch.Tensor, gt_classes: torch.T
                                       _ptr(out["seed_index"]), _ptr(out["seed_class"]), _ptr(out["seed_score"]),
                                       _ptr(out["gt_class"]), _ptr(out["gt_weight"]), _ptr(out["gt_index"]),
                                       _ptr(out["counts"]), _ptr(ws), wsb, _stream()), "oicr_mine_label")
+    _count(2)
     return out
 
 
@@ -275,6 +294,7 @@ def oicr_loss(logits: torch.Tensor, col_ref0: int, ref_stride: int, boxes: torch
                                         int(flip_quirk), *[float(x) for x in weights], _ptr(losses), _ptr(view_losses),
                                         _ptr(acc), _ptr(dlogits), 0 if dlogits is None else dlogits.stride(0),
                                         _stream()), "oicr_loss")
+    _count(2)
     return losses, view_losses, acc
 
 
@@ -289,6 +309,7 @@ def predict(logits: torch.Tensor, col_ref0: int, ref_stride: int, boxes: torch.T
     pred_boxes = torch.empty((R, 4 * C), dtype=torch.float32, device=logits.device)
     check(_lib.load().soswsod_predict(_ptr(logits), logits.stride(0), col_ref0, ref_stride, _ptr(boxes.contiguous()), R, C,
                                       K, *[float(x) for x in weights], _ptr(probs), _ptr(pred_boxes), _stream()), "predict")
+    _count(1)
     return probs, pred_boxes
 
 
@@ -300,6 +321,7 @@ def tta_accumulate(pred_boxes: torch.Tensor, probs: torch.Tensor, scale_x: float
     check(_lib.load().soswsod_tta_accumulate(_ptr(pred_boxes.contiguous()), _ptr(probs.contiguous()), R, C, float(scale_x),
                                              float(scale_y), int(flipped), float(view_w), int(first), float(finalize_div),
                                              _ptr(acc_boxes), _ptr(acc_probs), _stream()), "tta_accumulate")
+    _count(1)
 
 
 def nms(boxes: torch.Tensor, scores: torch.Tensor, iou_thr: float) -> torch.Tensor:
@@ -317,6 +339,7 @@ def nms(boxes: torch.Tensor, scores: torch.Tensor, iou_thr: float) -> torch.Tens
     ws = torch.empty((wsb,), dtype=torch.uint8, device=boxes.device)
     check(lib.soswsod_nms(_ptr(boxes), _ptr(scores), n, float(iou_thr), _ptr(keep), _ptr(num), _ptr(ws), wsb, _stream()),
           "nms")
+    _count(4)
     return keep[: int(num.item())]
 
 
@@ -340,4 +363,5 @@ def detect(probs: torch.Tensor, pred_boxes: torch.Tensor, image_size: Tuple[floa
     check(lib.soswsod_detect(_ptr(probs.contiguous()), _ptr(pred_boxes.contiguous()), R, C, float(image_size[0]),
                              float(image_size[1]), float(score_thr), float(nms_thr), int(topk), _ptr(db), _ptr(ds),
                              _ptr(dc), _ptr(dr), _ptr(nd), _ptr(workspace), workspace.numel(), _stream()), "detect")
+    _count(5)
     return db, ds, dc, dr, nd

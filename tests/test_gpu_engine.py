@@ -1,0 +1,262 @@
+"""GPU parity of the fused head step (engine + OICRPlusHeads plugin surface) against the CPU oracle's
+train_step / test_forward (oracle/oicr_plus_ref.py, restating roi_heads_oicrplus.py:190-475).
+
+Tolerances (BASELINE.json north_star): GEMM-derived scores <= 1e-2 relative, losses within 1e-3; integer results
+(pseudo-labels, assignment indices) bit-exact GIVEN IDENTICAL fp32 scores -- the oracle is therefore fed the
+engine's own view-averaged scores through `prev_override`, and must then reproduce the engine's labels exactly."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import oicr_plus_ref as ref
+
+pytestmark = pytest.mark.gpu
+
+
+def _small_setup(R=300, C=20, K=3, ch=64, fc=512, seed=0, sizes=((240, 320), (288, 384))):
+    from sos_wsod_b200.engine import HeadConfig, HeadOperands, OICRPlusHeadEngine, ViewBatch
+
+    g = torch.Generator().manual_seed(seed)
+    views = ref.synth_views(R, list(sizes), g, channels=ch)
+    p = ref.init_head_params(C, K, in_dim=ch * 49, fc_dim=fc, generator=g)
+    # larger head weights than the reference init so that scores/labels are not degenerate on random features
+    for t in (p.cls_w, p.det_w):
+        t.mul_(3.0)
+    for r in p.refine:
+        r[0].mul_(20.0)
+        r[2].mul_(20.0)
+    gt_classes = torch.tensor([3, 3, 7, 12])
+    cfg = HeadConfig(num_classes=C, refine_k=K, in_channels=ch, fc_dim=fc)
+    dev = "cuda"
+    pd = [t.to(dev) for t in (p.fc1_w, p.fc1_b, p.fc2_w, p.fc2_b, p.cls_w, p.cls_b, p.det_w, p.det_b)]
+    refine = [tuple(t.to(dev) for t in r) for r in p.refine]
+    op = HeadOperands(cfg, *pd, refine)
+    eng = OICRPlusHeadEngine(cfg, op)
+    feats = [torch.cat([views[0].feat, views[1].feat], 0).to(dev), torch.cat([views[2].feat, views[3].feat], 0).to(dev)]
+    rois = []
+    for a, b in ((0, 1), (2, 3)):
+        r0 = torch.cat([torch.zeros(R, 1), views[a].boxes], 1)
+        r1 = torch.cat([torch.ones(R, 1), views[b].boxes], 1)
+        rois.append(torch.cat([r0, r1], 0).to(dev))
+    obj = torch.cat([v.obj for v in views]).to(dev)
+    vb = ViewBatch(feats, rois, obj, R)
+    return eng, vb, views, p, gt_classes, cfg
+
+
+def _rel_err(a, b):
+    return (a - b).norm().item() / max(b.norm().item(), 1e-30)
+
+
+@pytest.mark.parametrize("dropout", [0.0, 0.5])
+def test_train_step_matches_oracle(cuda_lib, dropout):
+    from sos_wsod_b200 import ops
+
+    eng, vb, views, p, gt_classes, cfg = _small_setup()
+    cfg.dropout_p = dropout
+    R, C, K, V = vb.R, cfg.num_classes, cfg.refine_k, 4
+    gt_int = torch.unique(gt_classes)
+    seeds = (11, 22)
+    out = eng.train_step(vb, gt_int.cuda(), dropout_seeds=seeds)
+    torch.cuda.synchronize()
+
+    drop_masks = None
+    if dropout > 0:
+        m1 = ops.dropout_mask(V * R, cfg.fc_dim, dropout, seeds[0]).cpu().float()
+        m2 = ops.dropout_mask(V * R, cfg.fc_dim, dropout, seeds[1]).cpu().float()
+        drop_masks = [(m1[v * R:(v + 1) * R], m2[v * R:(v + 1) * R]) for v in range(V)]
+    p.requires_grad_(True)
+    for v in views:
+        v.feat.requires_grad_(True)
+    prev_dev = out.aux["prev"].cpu()
+    prev_override = [prev_dev[0][:, :C]] + [prev_dev[k] for k in range(1, K)]
+    exp_losses, aux = ref.train_step(views, gt_classes, p, C, K, drop_masks=drop_masks, prev_override=prev_override)
+    sum(exp_losses.values()).backward()
+
+    # losses within 1e-3
+    for k, v in exp_losses.items():
+        assert abs(out.losses[k].item() - v.item()) < 1e-3, (k, out.losses[k].item(), v.item())
+    # WSDDN scores: <= 1e-2 relative (bf16 GEMM chain)
+    for vi in range(V):
+        assert _rel_err(out.aux["scores"][vi].cpu(), aux["wsddn_scores"][vi]) < 1e-2
+    # the view-averaged scores the next branch mines from
+    for k in range(K - 1):
+        assert _rel_err(prev_dev[k + 1], aux["branches"][k]["next_prev"]) < 1e-2
+    # given identical scores, the labels / weights / matched seed indices are bit-exact
+    for k in range(K):
+        b = aux["branches"][k]
+        M = int(out.aux["seed_count"][k].item())
+        assert torch.equal(out.aux["seed_index"][k, :M].cpu().long(), b["seeds"].index)
+        assert torch.equal(out.aux["gt_class"][k].cpu().long(), b["gt_classes"])
+        assert torch.equal(out.aux["gt_index"][k].cpu().long(), b["gt_index"])
+        assert torch.equal(out.aux["gt_weight"][k].cpu(), b["gt_weights"])
+    # gradients (bf16 operands, fp32 accumulation): relative Frobenius error
+    exp_g = {"fc1_w": p.fc1_w.grad, "fc1_b": p.fc1_b.grad, "fc2_w": p.fc2_w.grad, "fc2_b": p.fc2_b.grad,
+             "cls_w": p.cls_w.grad, "cls_b": p.cls_b.grad, "det_w": p.det_w.grad, "det_b": p.det_b.grad}
+    for k in range(K):
+        exp_g.update({f"r{k}_cls_w": p.refine[k][0].grad, f"r{k}_cls_b": p.refine[k][1].grad,
+                      f"r{k}_box_w": p.refine[k][2].grad, f"r{k}_box_b": p.refine[k][3].grad})
+    for name, eg in exp_g.items():
+        err = _rel_err(out.grads[name].cpu().float(), eg)
+        assert err < 3e-2, (name, err)
+    gf1 = torch.cat([views[0].feat.grad, views[1].feat.grad], 0)
+    gf2 = torch.cat([views[2].feat.grad, views[3].feat.grad], 0)
+    assert _rel_err(out.grad_feats[0].cpu(), gf1) < 3e-2
+    assert _rel_err(out.grad_feats[1].cpu(), gf2) < 3e-2
+    assert eng.launches_last_step >= 20
+
+
+def test_test_forward_and_detect_match_oracle(cuda_lib):
+    eng, vb, views, p, gt_classes, cfg = _small_setup(R=400, seed=5)
+    C, K = cfg.num_classes, cfg.refine_k
+    probs, pboxes = eng.test_forward(vb)
+    for vi, v in enumerate(views):
+        ep, eb = ref.test_forward(v, p, C, K)
+        assert _rel_err(probs[vi].cpu(), ep) < 1e-2
+        assert _rel_err(pboxes[vi].cpu(), eb) < 1e-2
+    # detection on the engine's own fp32 probabilities/boxes must equal the oracle's inference exactly
+    db, ds, dc, dr, nd = eng.detect(probs[0], pboxes[0], views[0].image_size)
+    eb_, es_, ec_, er_ = ref.fast_rcnn_inference_single_image(pboxes[0].cpu(), probs[0].cpu(), views[0].image_size,
+                                                             cfg.score_thresh_test, cfg.nms_thresh_test,
+                                                             cfg.detections_per_image)
+    n = int(nd.item())
+    assert n == es_.numel()
+    assert torch.equal(dr[:n].cpu().long(), er_) and torch.equal(dc[:n].cpu().long(), ec_)
+    assert torch.equal(ds[:n].cpu(), es_) and torch.equal(db[:n].cpu(), eb_)
+
+
+def test_tta_detect_matches_oracle(cuda_lib):
+    eng, vb, views, p, gt_classes, cfg = _small_setup(R=250, seed=6)
+    C = cfg.num_classes
+    (h1, w1), (h2, w2) = views[0].image_size, views[2].image_size
+    tf = [(1.0, 1.0, False, float(w1)), (1.0, 1.0, True, float(w1)), (w1 / w2, h1 / h2, False, float(w2)),
+          (w1 / w2, h1 / h2, True, float(w2))]
+    det, acc_p, acc_b = eng.tta_detect(vb, tf, (h1, w1))
+    probs, pboxes = eng.test_forward(vb)
+    eb = [ref.tta_inverse_boxes(pboxes[v].cpu().reshape(-1, 4), *tf[v]).reshape(vb.R, 4 * C) for v in range(4)]
+    mb, mp = ref.tta_merge(eb, [probs[v].cpu() for v in range(4)])
+    torch.testing.assert_close(acc_b.cpu(), mb, rtol=1e-5, atol=1e-3)
+    torch.testing.assert_close(acc_p.cpu(), mp, rtol=1e-5, atol=1e-7)
+    # all four views describe the same boxes -> after inverse transforms the merged boxes are close to view 0's
+    db, ds, dc, dr, nd = det
+    e = ref.fast_rcnn_inference_single_image(acc_b.cpu(), acc_p.cpu(), (h1, w1), cfg.score_thresh_test,
+                                             cfg.nms_thresh_test, cfg.detections_per_image)
+    n = int(nd.item())
+    assert torch.equal(dr[:n].cpu().long(), e[3]) and torch.equal(ds[:n].cpu(), e[1])
+
+
+def test_plugin_surface_train_and_eval(cuda_lib):
+    """OICRPlusHeads built from config through the registry: forward(images, features, proposals, targets) returns
+    the reference's loss keys, backward fills .grad of every parameter with the engine's gradients, eval returns
+    (instances, {}, all_scores, all_boxes)."""
+    from sos_wsod_b200.config import get_cfg
+    from sos_wsod_b200.modeling import build_roi_heads
+    from sos_wsod_b200.structures import Boxes, Instances, ShapeSpec
+
+    torch.manual_seed(0)
+    cfg = get_cfg()
+    cfg.MODEL.ROI_BOX_HEAD.DAN_DIM = [256, 256]
+    ch, R, C, K = 32, 200, 20, 3
+    heads = build_roi_heads(cfg, {"plain5": ShapeSpec(channels=ch, stride=8)}).cuda()
+    for r in heads.box_refinery:
+        r.cls_score.weight.data.mul_(20.0)
+    g = torch.Generator().manual_seed(3)
+    views = ref.synth_views(R, [(240, 320), (288, 384)], g, channels=ch)
+    f1 = torch.cat([views[0].feat, views[1].feat], 0).cuda().requires_grad_(True)
+    f2 = torch.cat([views[2].feat, views[3].feat], 0).cuda().requires_grad_(True)
+
+    def props(v):
+        return [Instances(v.image_size, proposal_boxes=Boxes(v.boxes.cuda()), objectness_logits=v.obj.cuda())]
+
+    targets = [Instances(views[0].image_size, gt_classes=torch.tensor([2, 9, 9]).cuda(),
+                         gt_boxes=Boxes(torch.zeros(3, 4).cuda()))]
+    heads.train()
+    none, losses = heads(None, [{"plain5": f1}, {"plain5": f2}], [props(v) for v in views], [targets, None, None, None])
+    assert none is None
+    assert sorted(losses) == sorted(["loss_cls"] + [f"loss_cls_r{k}" for k in range(K)] + [f"loss_box_reg_r{k}" for k in range(K)])
+    total = sum(losses.values())
+    assert torch.isfinite(total)
+    total.backward()
+    out = heads.engine().last_output
+    for name, prm in heads.named_parameters():
+        assert prm.grad is not None and torch.isfinite(prm.grad).all(), name
+    assert torch.equal(heads.box_head.fc1.weight.grad, out.grads["fc1_w"])
+    assert torch.equal(heads.box_refinery_1.bbox_pred.weight.grad, out.grads["r1_box_w"])
+    assert f1.grad is not None and f1.grad.shape == f1.shape and float(f1.grad.abs().sum()) > 0
+    # an SGD step changes the master weights -> the bf16 operands refresh automatically on the next call
+    with torch.no_grad():
+        for prm in heads.parameters():
+            prm.add_(prm.grad, alpha=-1e-3)
+    _, losses2 = heads(None, [{"plain5": f1}, {"plain5": f2}], [props(v) for v in views], [targets, None, None, None])
+    assert abs(losses2["loss_cls"].item() - losses["loss_cls"].item()) > 0
+    # eval
+    heads.eval()
+    inst, empty, all_scores, all_boxes = heads(None, {"plain5": f1[:1].detach()}, props(views[0]), None)
+    assert empty == {} and all_scores.shape == (1, R, C + 1) and all_boxes.shape == (1, R, 4 * C)
+    assert len(inst) == 1 and len(inst[0].scores) <= cfg.TEST.DETECTIONS_PER_IMAGE
+    assert (inst[0].scores[:-1] >= inst[0].scores[1:]).all()
+
+
+def test_module_by_module_path(cuda_lib):
+    """The stand-alone sub-modules (box_pooler -> box_head -> box_predictor / box_refinery) compose like the
+    reference's and agree with the oracle within the bf16 tolerance, including gradients to the feature map."""
+    from sos_wsod_b200.config import get_cfg
+    from sos_wsod_b200.modeling import build_roi_heads
+    from sos_wsod_b200.structures import Boxes, Instances, ShapeSpec
+
+    torch.manual_seed(1)
+    cfg = get_cfg()
+    cfg.MODEL.ROI_BOX_HEAD.DAN_DIM = [256, 256]
+    ch, R, C = 16, 150, 20
+    heads = build_roi_heads(cfg, {"plain5": ShapeSpec(channels=ch, stride=8)}).cuda().eval()
+    g = torch.Generator().manual_seed(4)
+    views = ref.synth_views(R, [(240, 320), (288, 384)], g, channels=ch)
+    v = views[0]
+    feat = v.feat.cuda().requires_grad_(True)
+    pooled = heads.box_pooler([feat], [Boxes(v.boxes.cuda())])
+    x = heads.box_head(pooled)
+    scores, deltas = heads.box_predictor(x, None)
+    oh = torch.zeros(1, C).cuda()
+    oh[0, [1, 5]] = 1
+    loss = heads.box_predictor.losses((scores, deltas), None, oh)["loss_cls"]
+    logits, bd = heads.box_refinery[0](x)
+    (loss + logits.square().mean() + bd.square().mean()).backward()
+    # oracle
+    p = ref.HeadParams(*[t.detach().cpu() for t in (heads.box_head.fc1.weight, heads.box_head.fc1.bias,
+                                                    heads.box_head.fc2.weight, heads.box_head.fc2.bias,
+                                                    heads.box_predictor.cls.weight, heads.box_predictor.cls.bias,
+                                                    heads.box_predictor.det.weight, heads.box_predictor.det.bias)])
+    fe = v.feat.clone().requires_grad_(True)
+    import torchvision
+    ep = torchvision.ops.roi_pool(fe, ref.boxes_to_pooler_format([v.boxes]), (7, 7), 0.125)
+    assert torch.equal(pooled.detach().cpu(), ep.detach())
+    ex = ref.box_head(ep, p)
+    es = ref.wsddn_scores(ex, p)
+    el = ref.wsddn_loss(es, oh.cpu())
+    r0 = heads.box_refinery[0]
+    ez, ed = ref.refine_forward(ex, tuple(t.detach().cpu() for t in (r0.cls_score.weight, r0.cls_score.bias,
+                                                                     r0.bbox_pred.weight, r0.bbox_pred.bias)))
+    (el + ez.square().mean() + ed.square().mean()).backward()
+    assert _rel_err(x.detach().cpu(), ex.detach()) < 1e-2
+    assert _rel_err(scores.cpu(), es.detach()) < 1e-2
+    assert abs(loss.item() - el.item()) < 1e-3
+    assert _rel_err(feat.grad.cpu(), fe.grad) < 5e-2
+
+
+def test_full_size_fc6_against_torch_gemm(cuda_lib):
+    """BASELINE size (M = 4 x 2000 rows, K = 25088, N = 4096): the tcgen05 GEMM against torch's own GEMM on the same
+    bf16 operands (fp32 accumulate both), on a strided sample of rows -- a size-independent linearity property too:
+    gemm(2a, b) == 2 gemm(a, b) exactly in bf16/fp32."""
+    from sos_wsod_b200 import ops
+
+    g = torch.Generator(device="cuda").manual_seed(0)
+    M, K, N = 8000, 25088, 4096
+    a = (torch.randn((M, K), generator=g, device="cuda") * 0.5).relu_().to(torch.bfloat16)
+    b = (torch.randn((N, K), generator=g, device="cuda") * 0.005).to(torch.bfloat16)
+    bias = torch.full((N,), 0.1, device="cuda")
+    y = ops.gemm_bf16(a, b, out_dtype=torch.float32, bias=bias)
+    rows = torch.arange(0, M, 37, device="cuda")
+    exp = a[rows].float() @ b.float().t() + bias
+    torch.testing.assert_close(y[rows], exp, rtol=2e-3, atol=2e-3)
+    y2 = ops.gemm_bf16(a * 2, b, out_dtype=torch.float32)
+    y1 = ops.gemm_bf16(a, b, out_dtype=torch.float32)
+    assert torch.equal(y2, y1 * 2)
