@@ -96,7 +96,13 @@ def test_train_step_matches_oracle(cuda_lib, dropout):
         exp_g.update({f"r{k}_cls_w": p.refine[k][0].grad, f"r{k}_cls_b": p.refine[k][1].grad,
                       f"r{k}_box_w": p.refine[k][2].grad, f"r{k}_box_b": p.refine[k][3].grad})
     for name, eg in exp_g.items():
-        err = _rel_err(out.grads[name].cpu().float(), eg)
+        got = out.grads[name].cpu().float()
+        if name == "det_b":
+            # softmax over proposals: the column sums of d loss / d det-logits vanish identically, so the true
+            # gradient is 0 and both sides hold only rounding noise -> absolute bound relative to cls_b's scale
+            assert got.abs().max().item() < 1e-3 * max(exp_g["cls_b"].abs().max().item(), 1e-6) + 1e-7, got
+            continue
+        err = _rel_err(got, eg)
         assert err < 3e-2, (name, err)
     gf1 = torch.cat([views[0].feat.grad, views[1].feat.grad], 0)
     gf2 = torch.cat([views[2].feat.grad, views[3].feat.grad], 0)
