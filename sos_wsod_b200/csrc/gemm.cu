@@ -17,9 +17,8 @@
 // Operand layouts in shared memory are the canonical UMMA layouts: K-major SWIZZLE_128B (rows of 64 bf16 =
 // 128 B, 8-row swizzle atoms, SBO = 1024 B) or MN-major SWIZZLE_128B (64 MN elements contiguous per k row,
 // 8-k-row atoms, SBO = 1024 B, LBO = BLOCK_K*128 B between 64-wide MN chunks).
-#include <cuda.h>
-
 #include "common.cuh"
+#include "tma.cuh"
 
 namespace soswsod {
 
@@ -35,36 +34,7 @@ __host__ __device__ constexpr int gemm_smem_bytes(int block_n) {
     return gemm_stages(block_n) * gemm_stage_bytes(block_n) + 1024 /*align slack*/ + 256 /*barriers*/;
 }
 
-// ---- PTX wrappers ---------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "WAIT_LOOP:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra WAIT_DONE;\n\t"
-        "bra WAIT_LOOP;\n\t"
-        "WAIT_DONE:\n\t"
-        "}" ::"r"(bar), "r"(parity)
-        : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
-        "l"(map), "r"(bar), "r"(c0), "r"(c1)
-        : "memory");
-}
+// ---- PTX wrappers (mbarrier / TMA ones live in tma.cuh) -------------------------------------------
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_commit(uint32_t bar) {
@@ -401,48 +371,6 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 }
 
 // ---- host side -------------------------------------------------------------------------------------
-typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static PFN_encodeTiled get_encode_fn() {
-    static PFN_encodeTiled fn = nullptr;
-    static bool tried = false;
-    if (!tried) {
-        tried = true;
-        void* p = nullptr;
-        cudaDriverEntryPointQueryResult qres;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
-            qres == cudaDriverEntryPointSuccess)
-            fn = reinterpret_cast<PFN_encodeTiled>(p);
-    }
-    return fn;
-}
-
-// 2-D bf16 tensor map over a row-major [rows, cols] matrix with leading dimension ld (elements);
-// box = {box_cols (inner), box_rows}, 128B swizzle.
-static int make_tmap(CUtensorMap* map, const void* base, long long rows, long long cols, long long ld, int box_cols,
-                     int box_rows) {
-    PFN_encodeTiled enc = get_encode_fn();
-    if (!enc) {
-        set_error("gemm: cuTensorMapEncodeTiled not available from the driver");
-        return SOSWSOD_ERR_CUDA;
-    }
-    cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-    cuuint64_t gstride[1] = {(cuuint64_t)ld * 2};
-    cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
-    cuuint32_t estr[2] = {1, 1};
-    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) {
-        set_error("gemm: cuTensorMapEncodeTiled failed with CUresult %d (rows=%lld cols=%lld ld=%lld box=%dx%d)", (int)r,
-                  rows, cols, ld, box_cols, box_rows);
-        return SOSWSOD_ERR_CUDA;
-    }
-    return SOSWSOD_OK;
-}
-
 int device_num_sms();
 
 template <int BLOCK_N, bool A_MN, bool B_MN, bool OUT_BF16>
@@ -490,11 +418,11 @@ extern "C" int soswsod_gemm_bf16(const void* a, long long lda, int a_mn_major, c
     const int block_n = (n <= 128 || (n > 256 && n <= 384) || ((m + kBlockM - 1) / kBlockM) * ((n + 255) / 256) < 96) ? 128 : 256;
     CUtensorMap ta, tb;
     int rc;
-    if (!a_mn_major) rc = make_tmap(&ta, a, m, k, lda, kBlockK, kBlockM);
-    else rc = make_tmap(&ta, a, k, m, lda, 64, kBlockK);
+    if (!a_mn_major) rc = make_tmap_2d(&ta, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a, m, k, lda, kBlockK, kBlockM, CU_TENSOR_MAP_SWIZZLE_128B);
+    else rc = make_tmap_2d(&ta, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a, k, m, lda, 64, kBlockK, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
-    if (!b_mn_major) rc = make_tmap(&tb, b, n, k, ldb, kBlockK, block_n);
-    else rc = make_tmap(&tb, b, k, n, ldb, 64, kBlockK);
+    if (!b_mn_major) rc = make_tmap_2d(&tb, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, b, n, k, ldb, kBlockK, block_n, CU_TENSOR_MAP_SWIZZLE_128B);
+    else rc = make_tmap_2d(&tb, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, b, k, n, ldb, 64, kBlockK, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
     GemmEpilogue ep;
     ep.bias = bias;

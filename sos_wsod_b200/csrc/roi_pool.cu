@@ -1,8 +1,8 @@
 // ROI max-pool forward / backward for sm_100a (kernel (1) of the hot path).
 //
 // Forward: a CTA stages CT channel planes of one image in shared memory (fp32, exact), then its warps
-// walk the ROIs of the CTA's chunk independently.  Inside a warp the 32 lanes are CT channels x S
-// sub-lanes (S = 32/CT); plane stride == S (mod 32) makes every shared-memory read conflict-free.
+// walk the ROIs of the CTA's chunk independently.  Inside a warp a lane owns one bin column of the ROI and
+// loops over (channel, bin row) pairs (see roi_pool_fwd_kernel).
 // Results of one ROI (CT*PH*PW values + argmax) are staged per warp and written out coalesced, as raw
 // fp32 (bit-equal to torchvision), as argmax (int32 / uint16) and as the bf16 fc6 operand already
 // multiplied by (objectness + 1).
@@ -17,6 +17,7 @@
 // uwsod/projects/WSL/wsl/layers/csrc/ROILoopPool/ROILoopPool_cuda.cu:77-137): C round() of the fp32
 // product, fp32 bin size, floor/ceil, clamp, strict '>' scan in row-major order, empty bin -> (0, -1).
 #include "common.cuh"
+#include "tma.cuh"
 
 namespace soswsod {
 
@@ -43,6 +44,14 @@ __device__ __forceinline__ RoiGeom roi_geometry(const float* __restrict__ roi, f
     return g;
 }
 
+constexpr int kFwdMaxP = 16;  // pooled_h, pooled_w limit of the staged kernel (larger grids use the global kernel)
+
+// Lane mapping: lane = sub * PW + pw with nsub = 32 / PW sub-slots (PW = 7 -> 4 x 7 = 28 active lanes).  A lane owns
+// one bin COLUMN pw of the ROI and walks the (channel, ph) pairs p = sub, sub + nsub, ... of the CTA's CT channels
+// (c = p % CT, ph = p / CT), so its column range [ws, we) is loop-invariant and lanes of one step share ph.  Per
+// bin it keeps only a running row maximum (one FMNMX per cell) and the first row that raised the maximum; the
+// arg-max column is recovered by re-scanning that single row -- same result as the reference's strict '>' scan
+// in row-major order (first maximum wins), NaNs never win, the stored value is the cell's own bit pattern.
 template <int CT>
 __global__ void __launch_bounds__(kFwdThreads, 1)
 roi_pool_fwd_kernel(const float* __restrict__ feat, int C, int H, int W, const float* __restrict__ rois, int R,
@@ -50,12 +59,12 @@ roi_pool_fwd_kernel(const float* __restrict__ feat, int C, int H, int W, const f
                     float* __restrict__ out_f32, int32_t* __restrict__ argmax_i32,
                     uint16_t* __restrict__ argmax_u16, __nv_bfloat16* __restrict__ out_bf16, long long ld_bf16,
                     int plane_stride, int rois_per_cta) {
-    constexpr int S = 32 / CT;
     extern __shared__ __align__(16) float smem[];
     float* planes = smem;                                        // [CT][plane_stride]
     const int PP = PH * PW;
     float* stage_val = planes + CT * plane_stride;               // [kFwdWarps][CT*PP]
     int* stage_idx = reinterpret_cast<int*>(stage_val + kFwdWarps * CT * PP);
+    int* bounds_all = stage_idx + kFwdWarps * CT * PP;           // [kFwdWarps][4*kFwdMaxP]
 
     const int groups = C / CT;
     const int b = blockIdx.x / groups;
@@ -81,54 +90,63 @@ roi_pool_fwd_kernel(const float* __restrict__ feat, int C, int H, int W, const f
     __syncthreads();
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int cl = lane % CT;  // channel inside the group
-    const int sj = lane / CT;  // sub-lane inside the bin
-    const float* pl = planes + cl * plane_stride;
+    const int nsub = 32 / PW;
+    const int sub = lane / PW, pw = lane - sub * PW;
+    const bool active = sub < nsub;
     float* sv = stage_val + warp * CT * PP;
     int* si = stage_idx + warp * CT * PP;
+    int* bnd = bounds_all + warp * 4 * kFwdMaxP;
     const int n_out = CT * PP;
+    const int npairs = CT * PH;
 
     const int r_begin = blockIdx.y * rois_per_cta;
     const int r_end = min(R, r_begin + rois_per_cta);
     for (int r = r_begin + warp; r < r_end; r += kFwdWarps) {
         const RoiGeom g = roi_geometry(rois + (size_t)r * 5, scale, PH, PW);
         if (g.batch != b) continue;  // warp-uniform
-        for (int ph = 0; ph < PH; ++ph) {
-            int hs = (int)floorf(__fmul_rn((float)ph, g.bin_h));
-            int he = (int)ceilf(__fmul_rn((float)(ph + 1), g.bin_h));
-            hs = min(max(hs + g.rs_h, 0), H);
-            he = min(max(he + g.rs_h, 0), H);
-            for (int pw = 0; pw < PW; ++pw) {
-                int ws = (int)floorf(__fmul_rn((float)pw, g.bin_w));
-                int we = (int)ceilf(__fmul_rn((float)(pw + 1), g.bin_w));
-                ws = min(max(ws + g.rs_w, 0), W);
-                we = min(max(we + g.rs_w, 0), W);
-                const bool empty = (he <= hs) || (we <= ws);
+        if (lane < PH) {
+            int hs = (int)floorf(__fmul_rn((float)lane, g.bin_h));
+            int he = (int)ceilf(__fmul_rn((float)(lane + 1), g.bin_h));
+            bnd[lane] = min(max(hs + g.rs_h, 0), H);
+            bnd[kFwdMaxP + lane] = min(max(he + g.rs_h, 0), H);
+        }
+        if (lane >= 16 && lane - 16 < PW) {
+            const int q = lane - 16;
+            int ws = (int)floorf(__fmul_rn((float)q, g.bin_w));
+            int we = (int)ceilf(__fmul_rn((float)(q + 1), g.bin_w));
+            bnd[2 * kFwdMaxP + q] = min(max(ws + g.rs_w, 0), W);
+            bnd[3 * kFwdMaxP + q] = min(max(we + g.rs_w, 0), W);
+        }
+        __syncwarp();
+        if (active) {
+            const int ws = bnd[2 * kFwdMaxP + pw], we = bnd[3 * kFwdMaxP + pw];
+            for (int p = sub; p < npairs; p += nsub) {
+                const int c = p % CT, ph = p / CT;
+                const int hs = bnd[ph], he = bnd[kFwdMaxP + ph];
+                const float* pl = planes + c * plane_stride;
                 float m = -FLT_MAX;
-                int idx = -1;
+                int bh = -1;
                 for (int h = hs; h < he; ++h) {
-                    const int rowoff = h * W;
-                    for (int w = ws + sj; w < we; w += S) {
-                        const float v = pl[rowoff + w];
-                        if (v > m) {
-                            m = v;
-                            idx = rowoff + w;
-                        }
+                    const float* row = pl + h * W;
+                    float rm = -FLT_MAX;
+                    for (int w = ws; w < we; ++w) rm = fmaxf(rm, row[w]);
+                    if (rm > m) {
+                        m = rm;
+                        bh = h;
                     }
                 }
-#pragma unroll
-                for (int off = CT; off < 32; off <<= 1) {
-                    const float om = __shfl_xor_sync(FULL_MASK, m, off);
-                    const int oi = __shfl_xor_sync(FULL_MASK, idx, off);
-                    if (om > m || (om == m && (unsigned)oi < (unsigned)idx)) {
-                        m = om;
-                        idx = oi;
-                    }
+                const bool empty = (he <= hs) || (we <= ws);
+                float outv = empty ? 0.f : -FLT_MAX;
+                int idx = -1;
+                if (bh >= 0) {
+                    const float* row = pl + bh * W;
+                    int w = ws;
+                    while (w < we - 1 && row[w] != m) ++w;
+                    outv = row[w];
+                    idx = bh * W + w;
                 }
-                if (sj == 0) {
-                    sv[cl * PP + ph * PW + pw] = empty ? 0.f : m;
-                    si[cl * PP + ph * PW + pw] = idx;
-                }
+                sv[c * PP + ph * PW + pw] = outv;
+                si[c * PP + ph * PW + pw] = idx;
             }
         }
         __syncwarp();
@@ -202,86 +220,174 @@ __global__ void roi_pool_fwd_global_kernel(const float* __restrict__ feat, int C
 // ------------------------------------------------------------------------------------------------
 // Backward
 // ------------------------------------------------------------------------------------------------
-constexpr int kBwdMaxWarps = 8;
+// A CTA owns the gradient planes of CT consecutive channels of one image (optionally only a band of rows of
+// them) in shared memory; consumer warp w is the ONLY writer of channel c0+w's plane, so there is no atomic and
+// no cross-warp race, and the accumulation order is fixed (deterministic).  A producer warp streams the
+// (roi, channel-group) tiles of argmax and grad_out through a TMA ring (cp.async.bulk.tensor + mbarriers): the
+// 98-byte per-channel runs of the [R, C*PH*PW] matrices are neither 16-byte aligned nor long enough for wide
+// loads, but a TMA box may start at any element.  Entries of one warp step that hit the same cell are
+// serialised by __match_any_sync rounds.
+constexpr int kBwdMaxCT = 8;
+constexpr int kBwdRT = 16;  // rois per ring stage
 
-template <typename GradT, typename ArgT>
-__device__ __forceinline__ void load_entry(const GradT* __restrict__ grad, long long ld_grad,
-                                           const ArgT* __restrict__ argmax, const float* __restrict__ rois,
-                                           const float* __restrict__ row_scale, float row_scale_bias, int N,
-                                           int b, int c, int C, int PP, long long i, long long total, int r0,
-                                           int& a, float& gval) {
-    a = -1;
-    gval = 0.f;
-    if (i >= total) return;
-    const int r = r0 + (int)(i / PP);
-    const int bin = (int)(i % PP);
-    if (N > 1 && (int)rois[(size_t)r * 5] != b) return;
-    const ArgT raw = argmax[((size_t)r * C + c) * PP + bin];
-    int av;
-    if (sizeof(ArgT) == 2)
-        av = ((unsigned)raw == 0xFFFFu) ? -1 : (int)(unsigned)raw;
-    else
-        av = (int)raw;
-    if (av < 0) return;
-    a = av;
-    float gv;
-    if (sizeof(GradT) == 2)
-        gv = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(&grad[(size_t)r * ld_grad + (size_t)c * PP + bin]));
-    else
-        gv = *reinterpret_cast<const float*>(&grad[(size_t)r * ld_grad + (size_t)c * PP + bin]);
-    const float s = row_scale ? __fadd_rn(row_scale[r], row_scale_bias) : 1.f;
-    gval = gv * s;
-}
+struct BwdCfg {
+    int CT, bands, band_rows, nbox, BW, stages;
+    int plane_stride;   // floats per plane band in smem
+    size_t smem;
+};
 
-template <typename GradT, typename ArgT>
-__global__ void __launch_bounds__(kBwdMaxWarps * 32, 1)
-roi_pool_bwd_kernel(const GradT* __restrict__ grad, long long ld_grad, const ArgT* __restrict__ argmax,
-                    const float* __restrict__ rois, int R, const float* __restrict__ row_scale,
-                    float row_scale_bias, int N, int C, int H, int W, int PP, float* __restrict__ grad_feat,
-                    int plane_stride) {
-    extern __shared__ __align__(16) float planes[];  // [nwarps][plane_stride]
-    const int nw = blockDim.x >> 5;
+template <typename GradT, typename ArgT, int PPT>
+__global__ void __launch_bounds__((kBwdMaxCT + 1) * 32, 1)
+roi_pool_bwd_kernel(const __grid_constant__ CUtensorMap tmap_arg, const __grid_constant__ CUtensorMap tmap_grad,
+                    const float* __restrict__ rois, int R, const float* __restrict__ row_scale, float row_scale_bias,
+                    int N, int C, int H, int W, int PP_rt, float* __restrict__ grad_feat, BwdCfg cfg) {
+    const int PP = PPT > 0 ? PPT : PP_rt;
+    extern __shared__ uint8_t smem_raw[];
+    const int CT = cfg.CT, BW = cfg.BW, nbox = cfg.nbox, S = cfg.stages;
+    const uint32_t base = (smem_u32(smem_raw) + 127u) & ~127u;
+    uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
+    float* planes = reinterpret_cast<float*>(gen_base);                          // [CT][plane_stride]
+    const uint32_t plane_bytes = (uint32_t)CT * cfg.plane_stride * 4;            // multiple of 128
+    const uint32_t arg_stage = (uint32_t)nbox * kBwdRT * BW * sizeof(ArgT);      // multiple of 128
+    const uint32_t grad_stage = (uint32_t)nbox * kBwdRT * BW * sizeof(GradT);
+    const uint32_t ring_off = plane_bytes;
+    const uint32_t bar_off = ring_off + S * (arg_stage + grad_stage);
+    auto full_bar = [&](int st) { return base + bar_off + 8u * st; };
+    auto empty_bar = [&](int st) { return base + bar_off + 8u * (S + st); };
+    int* s_range = reinterpret_cast<int*>(gen_base + bar_off + 16 * S);          // [2]
+
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int b = blockIdx.x / C, c = blockIdx.x % C;
+    const int groups = (C + CT - 1) / CT;
+    int bid = blockIdx.x;
+    const int band = bid % cfg.bands;
+    bid /= cfg.bands;
+    const int c0 = (bid % groups) * CT;
+    const int b = bid / groups;
     const int HW = H * W;
-    for (int i = threadIdx.x; i < nw * plane_stride; i += blockDim.x) planes[i] = 0.f;
+    const int band_lo = min(band * cfg.band_rows, H) * W;
+    const int band_hi = min((band + 1) * cfg.band_rows, H) * W;
+
+    for (int i = threadIdx.x; i < CT * cfg.plane_stride; i += blockDim.x) planes[i] = 0.f;
+    if (threadIdx.x == 0) {
+        for (int st = 0; st < S; ++st) {
+            mbar_init(full_bar(st), 1);
+            mbar_init(empty_bar(st), CT);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        s_range[0] = N > 1 ? R : 0;
+        s_range[1] = N > 1 ? 0 : R;
+    }
     __syncthreads();
+    if (N > 1) {  // rows of this image: [first, last+1) (exact when the rois are grouped by image, a superset otherwise)
+        int lo = R, hi = 0;
+        for (int r = threadIdx.x; r < R; r += blockDim.x)
+            if ((int)rois[(size_t)r * 5] == b) {
+                lo = min(lo, r);
+                hi = max(hi, r + 1);
+            }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lo = min(lo, __shfl_xor_sync(FULL_MASK, lo, o));
+            hi = max(hi, __shfl_xor_sync(FULL_MASK, hi, o));
+        }
+        if (lane == 0) {
+            atomicMin(&s_range[0], lo);   // integer bookkeeping only; gradients never go through an atomic
+            atomicMax(&s_range[1], hi);
+        }
+        __syncthreads();
+    }
+    const int r_lo = s_range[0], r_hi = s_range[1];
+    const int ntiles = r_hi > r_lo ? (r_hi - r_lo + kBwdRT - 1) / kBwdRT : 0;
 
-    float* my = planes + warp * plane_stride;
-    const int per = (R + nw - 1) / nw;
-    const int r0 = warp * per;
-    const int r1 = min(R, r0 + per);
-    const long long total = (r1 > r0) ? (long long)(r1 - r0) * PP : 0;
-
-    int a_nx;
-    float g_nx;
-    load_entry<GradT, ArgT>(grad, ld_grad, argmax, rois, row_scale, row_scale_bias, N, b, c, C, PP, lane, total,
-                            r0, a_nx, g_nx);
-    for (long long i0 = 0; i0 < total; i0 += 32) {
-        const int a = a_nx;
-        const float gval = g_nx;
-        // prefetch the next step's entry while this one is being applied
-        load_entry<GradT, ArgT>(grad, ld_grad, argmax, rois, row_scale, row_scale_bias, N, b, c, C, PP,
-                                i0 + 32 + lane, total, r0, a_nx, g_nx);
-        const bool valid = a >= 0;
-        const unsigned act = __ballot_sync(FULL_MASK, valid);
-        if (act == 0) continue;
-        unsigned peers = 0;
-        if (valid) peers = __match_any_sync(act, a);
-        unsigned pending = act;
-        while (pending) {
-            const bool lead = valid && ((pending >> lane) & 1u) && ((__ffs(peers & pending) - 1) == lane);
-            if (lead) my[a] += gval;
+    if (warp == CT) {
+        if (lane == 0) {
+            int st = 0;
+            uint32_t phase = 0;
+            for (int t = 0; t < ntiles; ++t) {
+                mbar_wait(empty_bar(st), phase ^ 1u);
+                mbar_expect_tx(full_bar(st), arg_stage + grad_stage);
+                const uint32_t sa = base + ring_off + st * (arg_stage + grad_stage);
+                const uint32_t sg = sa + arg_stage;
+                const int r0 = r_lo + t * kBwdRT;
+                for (int bx = 0; bx < nbox; ++bx) {
+                    tma_load_2d(sa + bx * (kBwdRT * BW * (int)sizeof(ArgT)), &tmap_arg, full_bar(st), c0 * PP + bx * BW, r0);
+                    tma_load_2d(sg + bx * (kBwdRT * BW * (int)sizeof(GradT)), &tmap_grad, full_bar(st), c0 * PP + bx * BW, r0);
+                }
+                if (++st == S) {
+                    st = 0;
+                    phase ^= 1u;
+                }
+            }
+        }
+    } else if (warp < CT) {
+        float* my = planes + warp * cfg.plane_stride;
+        const bool chan_ok = (c0 + warp) < C;
+        const int e0 = warp * PP;
+        int st = 0;
+        uint32_t phase = 0;
+        for (int t = 0; t < ntiles; ++t) {
+            mbar_wait(full_bar(st), phase);
+            const uint8_t* ring = gen_base + ring_off + (size_t)st * (arg_stage + grad_stage);
+            const ArgT* ta = reinterpret_cast<const ArgT*>(ring);
+            const GradT* tg = reinterpret_cast<const GradT*>(ring + arg_stage);
+            const int r0 = r_lo + t * kBwdRT;
+            const int nent = kBwdRT * PP;
+            for (int i0 = 0; i0 < nent; i0 += 32) {
+                const int i = i0 + lane;
+                int a = -1;
+                float gval = 0.f;
+                if (i < nent && chan_ok) {
+                    const int rr = i / PP, bin = i - rr * PP;
+                    const int r = r0 + rr;
+                    if (r < r_hi && (N == 1 || (int)rois[(size_t)r * 5] == b)) {
+                        const int e = e0 + bin;
+                        const int bx = e / BW, col = e - bx * BW;
+                        const int off = (bx * kBwdRT + rr) * BW + col;
+                        const ArgT raw = ta[off];
+                        int av;
+                        if (sizeof(ArgT) == 2)
+                            av = ((unsigned)raw == 0xFFFFu) ? -1 : (int)(unsigned)raw;
+                        else
+                            av = (int)raw;
+                        if (av >= band_lo && av < band_hi) {
+                            a = av - band_lo;
+                            float gv;
+                            if (sizeof(GradT) == 2)
+                                gv = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(&tg[off]));
+                            else
+                                gv = *reinterpret_cast<const float*>(&tg[off]);
+                            const float sc = row_scale ? __fadd_rn(row_scale[r], row_scale_bias) : 1.f;
+                            gval = gv * sc;
+                        }
+                    }
+                }
+                const bool valid = a >= 0;
+                const unsigned act = __ballot_sync(FULL_MASK, valid);
+                if (act == 0) continue;
+                unsigned peers = 0;
+                if (valid) peers = __match_any_sync(act, a);
+                unsigned pending = act;
+                while (pending) {
+                    const bool lead = valid && ((pending >> lane) & 1u) && ((__ffs(peers & pending) - 1) == lane);
+                    if (lead) my[a] += gval;
+                    __syncwarp();
+                    pending &= ~__ballot_sync(FULL_MASK, lead);
+                }
+            }
             __syncwarp();
-            pending &= ~__ballot_sync(FULL_MASK, lead);
+            if (lane == 0) mbar_arrive(empty_bar(st));
+            if (++st == S) {
+                st = 0;
+                phase ^= 1u;
+            }
         }
     }
     __syncthreads();
-    float* dst = grad_feat + ((size_t)b * C + c) * HW;
-    for (int i = threadIdx.x; i < HW; i += blockDim.x) {
-        float s = 0.f;
-        for (int w = 0; w < nw; ++w) s += planes[w * plane_stride + i];
-        dst[i] = s;
+    const int band_cells = band_hi - band_lo;
+    for (int c = 0; c < CT && c0 + c < C; ++c) {
+        float* dst = grad_feat + ((size_t)b * C + c0 + c) * HW + band_lo;
+        const float* src = planes + c * cfg.plane_stride;
+        for (int i = threadIdx.x; i < band_cells; i += blockDim.x) dst[i] = src[i];
     }
 }
 
@@ -390,13 +496,15 @@ extern "C" int soswsod_roi_pool_forward(const float* feat, int n, int c, int h, 
     const int max_smem = device_max_smem();
     // pick the largest channel group whose planes + staging fit
     const int cts[4] = {8, 4, 2, 1};
-    for (int k = 0; k < 4; ++k) {
+    for (int k = 0; k < 4 && pooled_h <= kFwdMaxP && pooled_w <= kFwdMaxP; ++k) {
         const int CT = cts[k];
         if (c % CT) continue;
-        const int S = 32 / CT;
-        int plane_stride = ((HW + 31) / 32) * 32 + (S % 32);
+        const int nsub = 32 / pooled_w;
+        // channel c sits c*(32/nsub) banks away from channel 0, so the nsub sub-slots of a warp step hit different banks
+        int plane_stride = ((HW + 31) / 32) * 32 + ((32 / nsub) % 32);
         if (CT == 1) plane_stride = ((HW + 3) / 4) * 4;
-        const size_t smem = (size_t)CT * plane_stride * 4 + (size_t)kFwdWarps * CT * PP * 8;
+        const size_t smem = (size_t)CT * plane_stride * 4 + (size_t)kFwdWarps * CT * PP * 8 +
+                            (size_t)kFwdWarps * 4 * kFwdMaxP * 4;
         if (smem > (size_t)max_smem) continue;
         switch (CT) {
             case 8: return launch_fwd<8>(feat, n, c, h, w, rois, num_rois, pooled_h, pooled_w, spatial_scale, row_scale, row_scale_bias, out_f32, a32, a16, obf, ld_bf16, plane_stride, smem, st);
@@ -416,25 +524,78 @@ extern "C" int soswsod_roi_pool_forward(const float* feat, int n, int c, int h, 
     return SOSWSOD_OK;
 }
 
+static bool pick_bwd_cfg(int n, int c, int h, int w, int PP, int arg_bytes, int grad_bytes, BwdCfg* out) {
+    const int max_smem = device_max_smem();
+    const int sms = device_num_sms();
+    bool found = false;
+    long long best_waves = 0;
+    for (int bands = 1; bands <= 64; ++bands) {
+        const int band_rows = (h + bands - 1) / bands;
+        if (bands > 1 && (long long)(bands - 1) * band_rows >= h) continue;  // empty last band
+        const int plane_stride = ((band_rows * w + 31) / 32) * 32;
+        for (int CT = kBwdMaxCT; CT >= 1; --CT) {
+            if (CT > c) continue;
+            const int cols = CT * PP;
+            const int nbox = (cols + 247) / 248;
+            const int BW = (((cols + nbox - 1) / nbox) + 7) / 8 * 8;
+            if (BW > 256) continue;
+            const size_t stage = (size_t)nbox * kBwdRT * BW * (arg_bytes + grad_bytes);
+            const size_t fixed = (size_t)CT * plane_stride * 4 + 128 /*align*/ + 256 /*barriers*/;
+            if (fixed + 2 * stage > (size_t)max_smem) continue;
+            int stages = (int)(((size_t)max_smem - fixed) / stage);
+            if (stages > 4) stages = 4;
+            const long long ctas = (long long)n * ((c + CT - 1) / CT) * bands;
+            const long long waves = (ctas + sms - 1) / sms;
+            if (!found || waves < best_waves) {
+                found = true;
+                best_waves = waves;
+                out->CT = CT;
+                out->bands = bands;
+                out->band_rows = band_rows;
+                out->nbox = nbox;
+                out->BW = BW;
+                out->stages = stages;
+                out->plane_stride = plane_stride;
+                out->smem = fixed + (size_t)stages * stage;
+            }
+        }
+        if (found && best_waves == 1) break;
+    }
+    return found;
+}
+
 template <typename GradT, typename ArgT>
 static int launch_bwd(const void* grad, long long ld_grad, const void* argmax, const float* rois, int R,
                       const float* row_scale, float bias, int n, int c, int h, int w, int PP, float* grad_feat,
                       cudaStream_t st) {
     const int HW = h * w;
-    const int plane_stride = ((HW + 3) / 4) * 4;
-    const int max_smem = device_max_smem();
-    int nw = max_smem / (plane_stride * 4);
-    if (nw > kBwdMaxWarps) nw = kBwdMaxWarps;
-    if (nw >= 1) {
-        const size_t smem = (size_t)nw * plane_stride * 4;
-        SOSWSOD_CHECK_CUDA(cudaFuncSetAttribute(roi_pool_bwd_kernel<GradT, ArgT>,
-                                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        roi_pool_bwd_kernel<GradT, ArgT><<<n * c, nw * 32, smem, st>>>(
-            (const GradT*)grad, ld_grad, (const ArgT*)argmax, rois, R, row_scale, bias, n, c, h, w, PP, grad_feat,
-            plane_stride);
+    BwdCfg cfg;
+    const bool aligned = ((uintptr_t)grad & 15) == 0 && ((uintptr_t)argmax & 15) == 0 &&
+                         ((ld_grad * (long long)sizeof(GradT)) & 15) == 0 && (((long long)c * PP * sizeof(ArgT)) & 15) == 0;
+    if (aligned && pick_bwd_cfg(n, c, h, w, PP, (int)sizeof(ArgT), (int)sizeof(GradT), &cfg)) {
+        CUtensorMap ta, tg;
+        int rc = make_tmap_2d(&ta, sizeof(ArgT) == 2 ? CU_TENSOR_MAP_DATA_TYPE_UINT16 : CU_TENSOR_MAP_DATA_TYPE_INT32,
+                              (int)sizeof(ArgT), argmax, R, (long long)c * PP, (long long)c * PP, cfg.BW, kBwdRT,
+                              CU_TENSOR_MAP_SWIZZLE_NONE);
+        if (rc) return rc;
+        rc = make_tmap_2d(&tg, sizeof(GradT) == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
+                          (int)sizeof(GradT), grad, R, (long long)c * PP, ld_grad, cfg.BW, kBwdRT, CU_TENSOR_MAP_SWIZZLE_NONE);
+        if (rc) return rc;
+        const int grid = n * ((c + cfg.CT - 1) / cfg.CT) * cfg.bands;
+        const int threads = (cfg.CT + 1) * 32;
+        if (PP == 49) {
+            auto kern = roi_pool_bwd_kernel<GradT, ArgT, 49>;
+            SOSWSOD_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem));
+            kern<<<grid, threads, cfg.smem, st>>>(ta, tg, rois, R, row_scale, bias, n, c, h, w, PP, grad_feat, cfg);
+        } else {
+            auto kern = roi_pool_bwd_kernel<GradT, ArgT, 0>;
+            SOSWSOD_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem));
+            kern<<<grid, threads, cfg.smem, st>>>(ta, tg, rois, R, row_scale, bias, n, c, h, w, PP, grad_feat, cfg);
+        }
         SOSWSOD_CHECK_LAUNCH();
         return SOSWSOD_OK;
     }
+    // misaligned inputs: zero + global atomics (documented fallback; not used by the head engine)
     SOSWSOD_CHECK_CUDA(cudaMemsetAsync(grad_feat, 0, (size_t)n * c * HW * 4, st));
     const long long total = (long long)R * c * PP;
     if (total == 0) return SOSWSOD_OK;
