@@ -96,7 +96,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
@@ -105,7 +105,17 @@ class ClockSampler:
 
     def _read(self):
         for ln in self.proc.stdout:
-            self.lines.append(ln.strip())
+            self.lines.append((time.perf_counter(), ln.strip()))
+
+    def wait_first_sample(self, timeout=15.0):
+        """nvidia-smi takes a second or two to attach to the driver (and slows CUDA calls while it does): the
+        timed region only starts once it is in its steady 200 ms polling loop."""
+        t0 = time.perf_counter()
+        while self.proc is not None and not self.lines and time.perf_counter() - t0 < timeout:
+            time.sleep(0.05)
+
+    def mark(self):
+        self.t_mark = time.perf_counter()
 
     def stop(self):
         if self.proc is None:
@@ -118,7 +128,10 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons, pw = [], [], set(), []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        t_mark = getattr(self, "t_mark", 0.0)
+        for ts, ln in self.lines:
+            if ts < t_mark:
+                continue
             parts = [p.strip() for p in ln.split(",")]
             if len(parts) < 7:
                 continue
@@ -292,11 +305,13 @@ def run_b200_arm(args):
             torch.cuda.synchronize()
 
     # ---- device-resident throughput ----
-    for i in range(args.warmup):
-        device_step(i)
-    sync_all()
     sampler = ClockSampler(local_rank)
     sampler.start()
+    for i in range(args.warmup):
+        device_step(i)
+    sampler.wait_first_sample()
+    sync_all()
+    sampler.mark()
     launches0 = ops.COUNTERS["launches"]
     record_gemm["on"] = True
     t_start = torch.cuda.Event(enable_timing=True)

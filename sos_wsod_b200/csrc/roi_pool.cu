@@ -44,6 +44,28 @@ __device__ __forceinline__ RoiGeom roi_geometry(const float* __restrict__ roi, f
     return g;
 }
 
+// One bin column of BWM cells over rows [hs, he): running row maximum (strict '>' keeps the FIRST best row).
+// `row` points at (hs, ws).  A lane whose own range is one cell narrower (shortlane) masks the last load; that load
+// is still inside the padded plane.
+template <int BWM>
+__device__ __forceinline__ void scan_rows(const float* __restrict__ row, int W, int hs, int he, bool shortlane,
+                                          float& m, int& bh) {
+#pragma unroll 2
+    for (int h = hs; h < he; ++h, row += W) {
+        float v[BWM];
+#pragma unroll
+        for (int j = 0; j < BWM; ++j) v[j] = row[j];
+        if (shortlane) v[BWM - 1] = -FLT_MAX;
+        float rm = v[0];
+#pragma unroll
+        for (int j = 1; j < BWM; ++j) rm = fmaxf(rm, v[j]);
+        if (rm > m) {
+            m = rm;
+            bh = h;
+        }
+    }
+}
+
 constexpr int kFwdMaxP = 16;  // pooled_h, pooled_w limit of the staged kernel (larger grids use the global kernel)
 
 // Lane mapping: lane = sub * PW + pw with nsub = 32 / PW sub-slots (PW = 7 -> 4 x 7 = 28 active lanes).  A lane owns
@@ -118,32 +140,55 @@ roi_pool_fwd_kernel(const float* __restrict__ feat, int C, int H, int W, const f
             bnd[3 * kFwdMaxP + q] = min(max(we + g.rs_w, 0), W);
         }
         __syncwarp();
+        // Column range of this lane; the widest range of the warp step picks ONE fully unrolled row scanner for
+        // every lane (uniform branch).  Lanes one cell narrower mask their last load; anything narrower still
+        // (bins clipped at the image border) takes the generic loop.
+        int ws = 0, bw = 0;
         if (active) {
-            const int ws = bnd[2 * kFwdMaxP + pw], we = bnd[3 * kFwdMaxP + pw];
+            ws = bnd[2 * kFwdMaxP + pw];
+            bw = max(bnd[3 * kFwdMaxP + pw] - ws, 0);
+        }
+        const int bwmax = (int)__reduce_max_sync(FULL_MASK, (unsigned)bw);
+        const bool fast = bw >= 1 && bw >= bwmax - 1 && bwmax <= 16;
+        const bool shortlane = bw < bwmax;
+        if (active) {
             for (int p = sub; p < npairs; p += nsub) {
                 const int c = p % CT, ph = p / CT;
                 const int hs = bnd[ph], he = bnd[kFwdMaxP + ph];
                 const float* pl = planes + c * plane_stride;
                 float m = -FLT_MAX;
                 int bh = -1;
-                for (int h = hs; h < he; ++h) {
-                    const float* row = pl + h * W;
-                    float rm = -FLT_MAX;
-                    for (int w = ws; w < we; ++w) rm = fmaxf(rm, row[w]);
-                    if (rm > m) {
-                        m = rm;
-                        bh = h;
+                if (bw > 0 && he > hs) {
+                    if (fast) {
+                        const float* row = pl + hs * W + ws;
+                        switch (bwmax) {
+#define SOSWSOD_SCAN(BWM) case BWM: scan_rows<BWM>(row, W, hs, he, shortlane, m, bh); break;
+                            SOSWSOD_SCAN(1) SOSWSOD_SCAN(2) SOSWSOD_SCAN(3) SOSWSOD_SCAN(4) SOSWSOD_SCAN(5) SOSWSOD_SCAN(6)
+                            SOSWSOD_SCAN(7) SOSWSOD_SCAN(8) SOSWSOD_SCAN(9) SOSWSOD_SCAN(10) SOSWSOD_SCAN(11)
+                            SOSWSOD_SCAN(12) SOSWSOD_SCAN(13) SOSWSOD_SCAN(14) SOSWSOD_SCAN(15) SOSWSOD_SCAN(16)
+#undef SOSWSOD_SCAN
+                        }
+                    } else {
+                        for (int h = hs; h < he; ++h) {
+                            const float* row = pl + h * W + ws;
+                            float rm = -FLT_MAX;
+                            for (int j = 0; j < bw; ++j) rm = fmaxf(rm, row[j]);
+                            if (rm > m) {
+                                m = rm;
+                                bh = h;
+                            }
+                        }
                     }
                 }
-                const bool empty = (he <= hs) || (we <= ws);
+                const bool empty = (he <= hs) || (bw <= 0);
                 float outv = empty ? 0.f : -FLT_MAX;
                 int idx = -1;
                 if (bh >= 0) {
-                    const float* row = pl + bh * W;
-                    int w = ws;
-                    while (w < we - 1 && row[w] != m) ++w;
-                    outv = row[w];
-                    idx = bh * W + w;
+                    const float* row = pl + bh * W + ws;
+                    int j = 0;
+                    while (j < bw - 1 && row[j] != m) ++j;
+                    outv = row[j];
+                    idx = bh * W + ws + j;
                 }
                 sv[c * PP + ph * PW + pw] = outv;
                 si[c * PP + ph * PW + pw] = idx;
@@ -225,13 +270,14 @@ __global__ void roi_pool_fwd_global_kernel(const float* __restrict__ feat, int C
 // no cross-warp race, and the accumulation order is fixed (deterministic).  A producer warp streams the
 // (roi, channel-group) tiles of argmax and grad_out through a TMA ring (cp.async.bulk.tensor + mbarriers): the
 // 98-byte per-channel runs of the [R, C*PH*PW] matrices are neither 16-byte aligned nor long enough for wide
-// loads, but a TMA box may start at any element.  Entries of one warp step that hit the same cell are
-// serialised by __match_any_sync rounds.
+// loads; a TMA box only needs its first column 16-byte aligned, so each box starts at the aligned column at or
+// below the group's first entry and the consumers add the remainder.  Entries of one warp step that hit the
+// same cell are serialised by __match_any_sync rounds.
 constexpr int kBwdMaxCT = 8;
-constexpr int kBwdRT = 16;  // rois per ring stage
+constexpr int kBwdMaxRT = 16;  // rois per ring stage (8 or 16)
 
 struct BwdCfg {
-    int CT, bands, band_rows, nbox, BW, stages;
+    int CT, bands, band_rows, nbox, BW, stages, RT;
     int plane_stride;   // floats per plane band in smem
     size_t smem;
 };
@@ -243,18 +289,20 @@ roi_pool_bwd_kernel(const __grid_constant__ CUtensorMap tmap_arg, const __grid_c
                     int N, int C, int H, int W, int PP_rt, float* __restrict__ grad_feat, BwdCfg cfg) {
     const int PP = PPT > 0 ? PPT : PP_rt;
     extern __shared__ uint8_t smem_raw[];
-    const int CT = cfg.CT, BW = cfg.BW, nbox = cfg.nbox, S = cfg.stages;
+    const int CT = cfg.CT, BW = cfg.BW, nbox = cfg.nbox, S = cfg.stages, RT = cfg.RT;
     const uint32_t base = (smem_u32(smem_raw) + 127u) & ~127u;
     uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
     float* planes = reinterpret_cast<float*>(gen_base);                          // [CT][plane_stride]
     const uint32_t plane_bytes = (uint32_t)CT * cfg.plane_stride * 4;            // multiple of 128
-    const uint32_t arg_stage = (uint32_t)nbox * kBwdRT * BW * sizeof(ArgT);      // multiple of 128
-    const uint32_t grad_stage = (uint32_t)nbox * kBwdRT * BW * sizeof(GradT);
+    const uint32_t arg_box = (uint32_t)RT * BW * sizeof(ArgT);                   // multiple of 128
+    const uint32_t grad_box = (uint32_t)RT * BW * sizeof(GradT);
+    const uint32_t arg_stage = nbox * arg_box, grad_stage = nbox * grad_box;
     const uint32_t ring_off = plane_bytes;
     const uint32_t bar_off = ring_off + S * (arg_stage + grad_stage);
     auto full_bar = [&](int st) { return base + bar_off + 8u * st; };
     auto empty_bar = [&](int st) { return base + bar_off + 8u * (S + st); };
     int* s_range = reinterpret_cast<int*>(gen_base + bar_off + 16 * S);          // [2]
+    float2* s_meta = reinterpret_cast<float2*>(s_range + 2);                     // [S][kBwdMaxRT] = (scale, 1 | 0 = skip this roi)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int groups = (C + CT - 1) / CT;
@@ -297,81 +345,109 @@ roi_pool_bwd_kernel(const __grid_constant__ CUtensorMap tmap_arg, const __grid_c
         __syncthreads();
     }
     const int r_lo = s_range[0], r_hi = s_range[1];
-    const int ntiles = r_hi > r_lo ? (r_hi - r_lo + kBwdRT - 1) / kBwdRT : 0;
+    const int ntiles = r_hi > r_lo ? (r_hi - r_lo + RT - 1) / RT : 0;
+    const int total_cols = C * PP;
+    const int col0 = c0 * PP;
+    const int col_a = col0 & ~(16 / (int)sizeof(ArgT) - 1);    // box start: 16-byte aligned column
+    const int col_g = col0 & ~(16 / (int)sizeof(GradT) - 1);
 
     if (warp == CT) {
-        if (lane == 0) {
-            int st = 0;
-            uint32_t phase = 0;
-            for (int t = 0; t < ntiles; ++t) {
-                mbar_wait(empty_bar(st), phase ^ 1u);
-                mbar_expect_tx(full_bar(st), arg_stage + grad_stage);
+        // ---- producer warp: lane 0 drives the barriers and TMA, lanes < RT publish each roi's scale / skip flag ----
+        uint32_t tx = 0;
+        for (int bx = 0; bx < nbox; ++bx) {
+            if (col_a + bx * BW < total_cols) tx += arg_box;
+            if (col_g + bx * BW < total_cols) tx += grad_box;
+        }
+        int st = 0;
+        uint32_t phase = 0;
+        for (int t = 0; t < ntiles; ++t) {
+            mbar_wait(empty_bar(st), phase ^ 1u);
+            const int r0 = r_lo + t * RT;
+            if (lane < RT) {
+                const int r = r0 + lane;
+                float2 meta = make_float2(0.f, 0.f);
+                if (r < r_hi && (N == 1 || (int)rois[(size_t)r * 5] == b))
+                    meta = make_float2(row_scale ? __fadd_rn(row_scale[r], row_scale_bias) : 1.f, 1.f);
+                s_meta[st * kBwdMaxRT + lane] = meta;
+            }
+            __syncwarp();
+            if (lane == 0) {
+                mbar_expect_tx(full_bar(st), tx);
                 const uint32_t sa = base + ring_off + st * (arg_stage + grad_stage);
                 const uint32_t sg = sa + arg_stage;
-                const int r0 = r_lo + t * kBwdRT;
                 for (int bx = 0; bx < nbox; ++bx) {
-                    tma_load_2d(sa + bx * (kBwdRT * BW * (int)sizeof(ArgT)), &tmap_arg, full_bar(st), c0 * PP + bx * BW, r0);
-                    tma_load_2d(sg + bx * (kBwdRT * BW * (int)sizeof(GradT)), &tmap_grad, full_bar(st), c0 * PP + bx * BW, r0);
+                    if (col_a + bx * BW < total_cols) tma_load_2d(sa + bx * arg_box, &tmap_arg, full_bar(st), col_a + bx * BW, r0);
+                    if (col_g + bx * BW < total_cols) tma_load_2d(sg + bx * grad_box, &tmap_grad, full_bar(st), col_g + bx * BW, r0);
                 }
-                if (++st == S) {
-                    st = 0;
-                    phase ^= 1u;
-                }
+            }
+            if (++st == S) {
+                st = 0;
+                phase ^= 1u;
             }
         }
     } else if (warp < CT) {
         float* my = planes + warp * cfg.plane_stride;
         const bool chan_ok = (c0 + warp) < C;
-        const int e0 = warp * PP;
+        const int ea0 = warp * PP + (col0 - col_a);
+        const int eg0 = warp * PP + (col0 - col_g);
+        const unsigned lt_mask = (1u << lane) - 1u;
+        const int nent = RT * PP;
         int st = 0;
         uint32_t phase = 0;
         for (int t = 0; t < ntiles; ++t) {
             mbar_wait(full_bar(st), phase);
-            const uint8_t* ring = gen_base + ring_off + (size_t)st * (arg_stage + grad_stage);
-            const ArgT* ta = reinterpret_cast<const ArgT*>(ring);
-            const GradT* tg = reinterpret_cast<const GradT*>(ring + arg_stage);
-            const int r0 = r_lo + t * kBwdRT;
-            const int nent = kBwdRT * PP;
-            for (int i0 = 0; i0 < nent; i0 += 32) {
-                const int i = i0 + lane;
-                int a = -1;
-                float gval = 0.f;
-                if (i < nent && chan_ok) {
-                    const int rr = i / PP, bin = i - rr * PP;
-                    const int r = r0 + rr;
-                    if (r < r_hi && (N == 1 || (int)rois[(size_t)r * 5] == b)) {
-                        const int e = e0 + bin;
-                        const int bx = e / BW, col = e - bx * BW;
-                        const int off = (bx * kBwdRT + rr) * BW + col;
-                        const ArgT raw = ta[off];
-                        int av;
-                        if (sizeof(ArgT) == 2)
-                            av = ((unsigned)raw == 0xFFFFu) ? -1 : (int)(unsigned)raw;
-                        else
-                            av = (int)raw;
-                        if (av >= band_lo && av < band_hi) {
-                            a = av - band_lo;
-                            float gv;
-                            if (sizeof(GradT) == 2)
-                                gv = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(&tg[off]));
+            if (chan_ok) {
+                const uint8_t* ring = gen_base + ring_off + (size_t)st * (arg_stage + grad_stage);
+                const ArgT* ta = reinterpret_cast<const ArgT*>(ring);
+                const GradT* tg = reinterpret_cast<const GradT*>(ring + arg_stage);
+                const float2* smeta = s_meta + st * kBwdMaxRT;
+                // entry i = rr*PP + bin; (rr, bin) advance by 32 entries per step without divisions
+                int rr = lane / PP, bin = lane - rr * PP;
+                for (int i0 = 0; i0 < nent; i0 += 32) {
+                    int a = -1;
+                    float gval = 0.f;
+                    if (rr < RT) {
+                        const float2 meta = smeta[rr];
+                        const float sc = meta.x;
+                        if (meta.y != 0.f) {
+                            int ea = ea0 + bin, eg = eg0 + bin;
+                            int offa = rr * BW, offg = rr * BW;
+                            if (ea >= BW) { ea -= BW; offa += RT * BW; }
+                            if (eg >= BW) { eg -= BW; offg += RT * BW; }
+                            const ArgT raw = ta[offa + ea];
+                            int av;
+                            if (sizeof(ArgT) == 2)
+                                av = ((unsigned)raw == 0xFFFFu) ? -1 : (int)(unsigned)raw;
                             else
-                                gv = *reinterpret_cast<const float*>(&tg[off]);
-                            const float sc = row_scale ? __fadd_rn(row_scale[r], row_scale_bias) : 1.f;
-                            gval = gv * sc;
+                                av = (int)raw;
+                            if (av >= band_lo && av < band_hi) {
+                                a = av - band_lo;
+                                float gv;
+                                if (sizeof(GradT) == 2)
+                                    gv = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(&tg[offg + eg]));
+                                else
+                                    gv = *reinterpret_cast<const float*>(&tg[offg + eg]);
+                                gval = gv * sc;
+                            }
                         }
                     }
-                }
-                const bool valid = a >= 0;
-                const unsigned act = __ballot_sync(FULL_MASK, valid);
-                if (act == 0) continue;
-                unsigned peers = 0;
-                if (valid) peers = __match_any_sync(act, a);
-                unsigned pending = act;
-                while (pending) {
-                    const bool lead = valid && ((pending >> lane) & 1u) && ((__ffs(peers & pending) - 1) == lane);
-                    if (lead) my[a] += gval;
-                    __syncwarp();
-                    pending &= ~__ballot_sync(FULL_MASK, lead);
+                    // lanes of this step that hit the same cell take turns in lane order (rank among their peers)
+                    const bool valid = a >= 0;
+                    const unsigned act = __ballot_sync(FULL_MASK, valid);
+                    if (valid) {
+                        const unsigned peers = __match_any_sync(act, a);
+                        const unsigned rank = __popc(peers & lt_mask);
+                        const unsigned rounds = __reduce_max_sync(act, rank);
+                        for (unsigned k = 0; k <= rounds; ++k) {
+                            if (rank == k) my[a] += gval;
+                            __syncwarp(act);
+                        }
+                    }
+                    bin += 32;
+                    while (bin >= PP) {
+                        bin -= PP;
+                        ++rr;
+                    }
                 }
             }
             __syncwarp();
@@ -502,7 +578,7 @@ extern "C" int soswsod_roi_pool_forward(const float* feat, int n, int c, int h, 
         const int nsub = 32 / pooled_w;
         // channel c sits c*(32/nsub) banks away from channel 0, so the nsub sub-slots of a warp step hit different banks
         int plane_stride = ((HW + 31) / 32) * 32 + ((32 / nsub) % 32);
-        if (CT == 1) plane_stride = ((HW + 3) / 4) * 4;
+        if (CT == 1) plane_stride = ((HW + 3) / 4) * 4 + 4;   // >= 1 float of padding after the last row
         const size_t smem = (size_t)CT * plane_stride * 4 + (size_t)kFwdWarps * CT * PP * 8 +
                             (size_t)kFwdWarps * 4 * kFwdMaxP * 4;
         if (smem > (size_t)max_smem) continue;
@@ -527,39 +603,46 @@ extern "C" int soswsod_roi_pool_forward(const float* feat, int n, int c, int h, 
 static bool pick_bwd_cfg(int n, int c, int h, int w, int PP, int arg_bytes, int grad_bytes, BwdCfg* out) {
     const int max_smem = device_max_smem();
     const int sms = device_num_sms();
+    const int align_elems = 16 / (arg_bytes < grad_bytes ? arg_bytes : grad_bytes);
     bool found = false;
-    long long best_waves = 0;
+    double best_cost = 0;
     for (int bands = 1; bands <= 64; ++bands) {
         const int band_rows = (h + bands - 1) / bands;
         if (bands > 1 && (long long)(bands - 1) * band_rows >= h) continue;  // empty last band
         const int plane_stride = ((band_rows * w + 31) / 32) * 32;
         for (int CT = kBwdMaxCT; CT >= 1; --CT) {
             if (CT > c) continue;
-            const int cols = CT * PP;
+            const int cols = CT * PP + align_elems - 1;   // + the alignment remainder of the first column
             const int nbox = (cols + 247) / 248;
             const int BW = (((cols + nbox - 1) / nbox) + 7) / 8 * 8;
-            if (BW > 256) continue;
-            const size_t stage = (size_t)nbox * kBwdRT * BW * (arg_bytes + grad_bytes);
-            const size_t fixed = (size_t)CT * plane_stride * 4 + 128 /*align*/ + 256 /*barriers*/;
-            if (fixed + 2 * stage > (size_t)max_smem) continue;
-            int stages = (int)(((size_t)max_smem - fixed) / stage);
-            if (stages > 4) stages = 4;
-            const long long ctas = (long long)n * ((c + CT - 1) / CT) * bands;
-            const long long waves = (ctas + sms - 1) / sms;
-            if (!found || waves < best_waves) {
-                found = true;
-                best_waves = waves;
-                out->CT = CT;
-                out->bands = bands;
-                out->band_rows = band_rows;
-                out->nbox = nbox;
-                out->BW = BW;
-                out->stages = stages;
-                out->plane_stride = plane_stride;
-                out->smem = fixed + (size_t)stages * stage;
+            if (BW > 256 || nbox > 2) continue;
+            const size_t fixed = (size_t)CT * plane_stride * 4 + 128 /*align*/ + 1024 /*barriers, roi meta*/;
+            for (int RT = kBwdMaxRT; RT >= 8; RT >>= 1) {
+                const size_t stage = (size_t)nbox * RT * BW * (arg_bytes + grad_bytes);
+                if (fixed + 2 * stage > (size_t)max_smem) continue;
+                int stages = (int)(((size_t)max_smem - fixed) / stage);
+                if (stages > 4) stages = 4;
+                const long long ctas = (long long)n * ((c + CT - 1) / CT) * bands;
+                const long long waves = (ctas + sms - 1) / sms;
+                // every CTA streams all rois of its image once: time ~ waves, with a mild preference for deeper rings
+                const double cost = (double)waves + (RT == 8 ? 0.05 : 0.0) + (stages < 3 ? 0.02 : 0.0);
+                if (!found || cost < best_cost - 1e-9) {
+                    found = true;
+                    best_cost = cost;
+                    out->CT = CT;
+                    out->bands = bands;
+                    out->band_rows = band_rows;
+                    out->nbox = nbox;
+                    out->BW = BW;
+                    out->stages = stages;
+                    out->RT = RT;
+                    out->plane_stride = plane_stride;
+                    out->smem = fixed + (size_t)stages * stage;
+                }
+                break;  // the largest RT that fits is enough for this (bands, CT)
             }
         }
-        if (found && best_waves == 1) break;
+        if (found && best_cost < 1.5) break;
     }
     return found;
 }
@@ -575,11 +658,11 @@ static int launch_bwd(const void* grad, long long ld_grad, const void* argmax, c
     if (aligned && pick_bwd_cfg(n, c, h, w, PP, (int)sizeof(ArgT), (int)sizeof(GradT), &cfg)) {
         CUtensorMap ta, tg;
         int rc = make_tmap_2d(&ta, sizeof(ArgT) == 2 ? CU_TENSOR_MAP_DATA_TYPE_UINT16 : CU_TENSOR_MAP_DATA_TYPE_INT32,
-                              (int)sizeof(ArgT), argmax, R, (long long)c * PP, (long long)c * PP, cfg.BW, kBwdRT,
+                              (int)sizeof(ArgT), argmax, R, (long long)c * PP, (long long)c * PP, cfg.BW, cfg.RT,
                               CU_TENSOR_MAP_SWIZZLE_NONE);
         if (rc) return rc;
         rc = make_tmap_2d(&tg, sizeof(GradT) == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
-                          (int)sizeof(GradT), grad, R, (long long)c * PP, ld_grad, cfg.BW, kBwdRT, CU_TENSOR_MAP_SWIZZLE_NONE);
+                          (int)sizeof(GradT), grad, R, (long long)c * PP, ld_grad, cfg.BW, cfg.RT, CU_TENSOR_MAP_SWIZZLE_NONE);
         if (rc) return rc;
         const int grid = n * ((c + cfg.CT - 1) / cfg.CT) * cfg.bands;
         const int threads = (cfg.CT + 1) * 32;

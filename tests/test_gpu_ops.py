@@ -121,6 +121,28 @@ def test_roi_pool_backward(ops, grad_bf16, argmax_u16):
     torch.testing.assert_close(gf.cpu(), feat.grad, rtol=1e-4, atol=1e-4)
 
 
+@pytest.mark.parametrize("C,h,w,N", [(16, 150, 200, 1), (8, 300, 260, 1), (24, 72, 96, 2), (10, 20, 30, 2)])
+def test_roi_pool_backward_plane_configs(ops, C, h, w, N):
+    """Planes that need fewer channels per CTA / several row bands / the misaligned-input fallback (C=10), and a
+    two-image batch with interleaved rois."""
+    import torchvision
+
+    g = _gen(50 + C)
+    R = 120
+    feat = torch.randn((N, C, h, w), generator=g).requires_grad_(True)
+    bl = [ref.synth_boxes(R, h * 8, w * 8, g) for _ in range(N)]
+    rois = ref.boxes_to_pooler_format(bl)
+    if N > 1:
+        rois = rois[torch.randperm(rois.size(0), generator=g)].contiguous()
+    pooled = torchvision.ops.roi_pool(feat, rois, (7, 7), 0.125)
+    go = torch.randn(pooled.shape, generator=g)
+    pooled.backward(go)
+    _, arg, _ = ops.roi_pool_forward(feat.detach().cuda(), rois.cuda(), want_f32=False)
+    assert torch.equal(arg.cpu(), ref.roi_pool(feat.detach(), rois)[1])
+    gf = ops.roi_pool_backward(go.flatten(1).cuda(), arg, rois.cuda(), (N, C, h, w))
+    torch.testing.assert_close(gf.cpu(), feat.grad, rtol=1e-4, atol=1e-4)
+
+
 # ------------------------------------------------------------------------------------------------
 # (2) GEMM
 # ------------------------------------------------------------------------------------------------
