@@ -1,0 +1,170 @@
+"""CPU suite, part 2: the C-ABI library loads and exports every symbol include/soswsod_b200.h declares (no compute
+calls without a GPU), the host-side plugin surface mirrors the reference's names, the product path refuses to run
+on CPU tensors (no fallback), and the data-parallel gradient hook averages over ranks (gloo, world_size 2)."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    hdr = open(os.path.join(ROOT, "include", "soswsod_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    return sorted(set(re.findall(r"\b(soswsod_[a-z0-9_]+)\s*\(", hdr)))
+
+
+def test_library_builds_and_exports_every_declared_symbol():
+    from sos_wsod_b200 import _lib
+    from sos_wsod_b200.build import build_library
+
+    path = build_library()
+    assert os.path.exists(path)
+    lib = ctypes.CDLL(path)
+    syms = _declared_symbols()
+    assert len(syms) >= 21, syms
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in include/soswsod_b200.h but not exported"
+    assert set(syms) == set(_lib.SIGNATURES), "ctypes prototypes and header must list the same entry points"
+    loaded = _lib.load()
+    assert loaded.soswsod_abi_version() == _lib.ABI_VERSION
+    assert loaded.soswsod_nms_workspace_bytes(2000) > 2000 * 32 * 8
+    assert loaded.soswsod_detect_workspace_bytes(2000, 20) > 20 * 2000 * 32 * 8
+    assert loaded.soswsod_oicr_mine_workspace_bytes(200, 3, 3) >= 3 * 600 * 12
+
+
+def test_sass_contains_blackwell_tensor_and_tma_instructions():
+    from sos_wsod_b200.build import LIB_PATH
+
+    out = subprocess.run(["cuobjdump", "-sass", LIB_PATH], capture_output=True, text=True).stdout
+    assert "UTCHMMA" in out, "tcgen05.mma must be present in the GEMM kernel"
+    assert "UTMALDG" in out, "TMA loads must be present"
+    assert "LDTM" in out, "tcgen05.ld (TMEM -> registers) must be present"
+    assert "sm_100a" in subprocess.run(["cuobjdump", "-lelf", LIB_PATH], capture_output=True, text=True).stdout
+
+
+def test_no_cpu_fallback():
+    from sos_wsod_b200 import ops
+
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ops.roi_pool_forward(torch.zeros(1, 4, 8, 8), torch.zeros(2, 5))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ops.nms(torch.zeros(3, 4), torch.zeros(3), 0.5)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ops.gemm_bf16(torch.zeros(8, 8, dtype=torch.bfloat16), torch.zeros(8, 8, dtype=torch.bfloat16))
+
+
+def test_missing_library_fails_loudly(tmp_path, monkeypatch):
+    from sos_wsod_b200 import _lib
+
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        _lib.load()
+
+
+def test_product_package_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "sos_wsod_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in src.replace("oracle/_ref", ""), f"{f} must not reference the oracle"
+
+
+def test_plugin_surface_names_match_reference():
+    from sos_wsod_b200.config import get_cfg
+    from sos_wsod_b200.modeling import OICRPlusHeads, build_roi_heads
+    from sos_wsod_b200.registry import ROI_BOX_HEAD_REGISTRY, ROI_HEADS_REGISTRY
+    from sos_wsod_b200.structures import ShapeSpec
+
+    cfg = get_cfg()
+    cfg.merge_from_list(["WSL.REFINE_NUM", 4])
+    assert ROI_HEADS_REGISTRY.get("OICRPlusHeads") is OICRPlusHeads
+    assert "DiscriminativeAdaptionNeck" in ROI_BOX_HEAD_REGISTRY
+    heads = build_roi_heads(cfg, {"plain5": ShapeSpec(channels=512, stride=8)})
+    names = dict(heads.named_parameters())
+    # checkpoint keys of the reference: shapes [out, in] fp32
+    assert names["box_head.fc1.weight"].shape == (4096, 25088) and names["box_head.fc2.weight"].shape == (4096, 4096)
+    assert names["box_predictor.cls.weight"].shape == (20, 4096) and names["box_predictor.det.bias"].shape == (20,)
+    for k in range(4):
+        assert names[f"box_refinery_{k}.cls_score.weight"].shape == (21, 4096)
+        assert names[f"box_refinery_{k}.bbox_pred.weight"].shape == (80, 4096)
+    assert len(names) == 8 + 4 * 4
+    # reference initialisers (box_head.py:64-67, fast_rcnn_oicr.py:465-468)
+    assert abs(names["box_head.fc1.weight"].std().item() - 0.005) < 2e-4
+    assert torch.all(names["box_head.fc1.bias"] == 0.1)
+    assert abs(names["box_refinery_0.cls_score.weight"].std().item() - 0.01) < 1e-3
+    hc = heads.head_config()
+    assert (hc.in_dim, hc.fc_dim, hc.refine_k, hc.head_cols) == (25088, 4096, 4, 2 * 20 + 4 * 101)
+    assert hc.top_k(2000) == 200 and hc.top_k(7) == 1
+    sd = heads.state_dict()
+    heads2 = build_roi_heads(cfg, {"plain5": ShapeSpec(channels=512, stride=8)})
+    heads2.load_state_dict(sd)
+
+
+def test_get_image_level_gt_and_structures():
+    from sos_wsod_b200.modeling import convert_boxes_to_pooler_format, get_image_level_gt
+    from sos_wsod_b200.structures import Boxes, Instances
+
+    t = [Instances((10, 10), gt_classes=torch.tensor([7, 2, 7]), gt_boxes=Boxes(torch.zeros(3, 4)))]
+    _, gt_int, oh = get_image_level_gt(t, 20)
+    assert gt_int[0].tolist() == [2, 7] and oh.shape == (1, 20) and oh.sum() == 2
+    r = convert_boxes_to_pooler_format([Boxes(torch.ones(2, 4)), Boxes(torch.zeros(1, 4))])
+    assert r.shape == (3, 5) and r[:, 0].tolist() == [0.0, 0.0, 1.0]
+    b = Boxes(torch.tensor([[-5.0, 2.0, 30.0, 50.0]]))
+    b.clip((20, 25))
+    assert b.tensor.tolist() == [[0.0, 2.0, 25.0, 20.0]]
+
+
+_DIST_SCRIPT = r'''
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%s" % sys.argv[2], rank=int(sys.argv[3]), world_size=2)
+rank = dist.get_rank()
+# the bench / trainer hook: start an async averaging all-reduce per layer as soon as its gradients exist
+works = []
+def grad_hook(name, tensors):
+    for t in tensors:
+        t.div_(dist.get_world_size())          # gloo has no AVG; NCCL path uses ReduceOp.AVG
+        works.append(dist.all_reduce(t, op=dist.ReduceOp.SUM, async_op=True))
+g = {"head": [torch.full((4, 3), float(rank + 1)), torch.full((4,), float(10 * (rank + 1)))],
+     "fc1": [torch.arange(6.0).reshape(2, 3) * (rank + 1)]}
+for name, ts in g.items():
+    grad_hook(name, ts)
+for w in works:
+    w.wait()
+assert torch.allclose(g["head"][0], torch.full((4, 3), 1.5)), g["head"][0]
+assert torch.allclose(g["head"][1], torch.full((4,), 15.0))
+assert torch.allclose(g["fc1"][0], torch.arange(6.0).reshape(2, 3) * 1.5)
+# image sharding of detection-result generation: contiguous blocks, no collective (InferenceSampler)
+n = 11
+per = (n + 1) // 2
+mine = list(range(rank * per, min(n, (rank + 1) * per)))
+gathered = [None, None]
+dist.all_gather_object(gathered, mine)
+assert sorted(sum(gathered, [])) == list(range(n))
+dist.destroy_process_group()
+print("rank", rank, "ok")
+'''
+
+
+def test_data_parallel_gradient_hook_gloo_world2(tmp_path):
+    script = tmp_path / "dp.py"
+    script.write_text(_DIST_SCRIPT)
+    import socket
+
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    procs = [subprocess.Popen([sys.executable, str(script), ROOT, str(port), str(r)], stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=120)[0] for p in procs]
+    for p, o in zip(procs, outs):
+        assert p.returncode == 0, o
