@@ -74,8 +74,10 @@ constexpr int kFwdMaxP = 16;  // pooled_h, pooled_w limit of the staged kernel (
 // bin it keeps only a running row maximum (one FMNMX per cell) and the first row that raised the maximum; the
 // arg-max column is recovered by re-scanning that single row -- same result as the reference's strict '>' scan
 // in row-major order (first maximum wins), NaNs never win, the stored value is the cell's own bit pattern.
-template <int CT>
-__global__ void __launch_bounds__(kFwdThreads, 1)
+// NT threads per CTA.  COMPACT (bf16 + uint16 outputs only -- the head engine's mode): results are staged as one
+// 32-bit word per bin (bf16 value << 16 | uint16 argmax), which leaves room for 32 warps per SM.
+template <int CT, int NT, bool COMPACT>
+__global__ void __launch_bounds__(NT, 1)
 roi_pool_fwd_kernel(const float* __restrict__ feat, int C, int H, int W, const float* __restrict__ rois, int R,
                     int PH, int PW, float scale, const float* __restrict__ row_scale, float row_scale_bias,
                     float* __restrict__ out_f32, int32_t* __restrict__ argmax_i32,
@@ -84,9 +86,11 @@ roi_pool_fwd_kernel(const float* __restrict__ feat, int C, int H, int W, const f
     extern __shared__ __align__(16) float smem[];
     float* planes = smem;                                        // [CT][plane_stride]
     const int PP = PH * PW;
-    float* stage_val = planes + CT * plane_stride;               // [kFwdWarps][CT*PP]
-    int* stage_idx = reinterpret_cast<int*>(stage_val + kFwdWarps * CT * PP);
-    int* bounds_all = stage_idx + kFwdWarps * CT * PP;           // [kFwdWarps][4*kFwdMaxP]
+    constexpr int kWarps = NT / 32;
+    float* stage_val = planes + CT * plane_stride;               // [kWarps][CT*PP] (COMPACT: packed words)
+    int* stage_idx = reinterpret_cast<int*>(stage_val + kWarps * CT * PP);   // generic mode only
+    int* bounds_all = COMPACT ? reinterpret_cast<int*>(stage_val + kWarps * CT * PP)
+                              : stage_idx + kWarps * CT * PP;    // [kWarps][4*kFwdMaxP]
 
     const int groups = C / CT;
     const int b = blockIdx.x / groups;
@@ -101,11 +105,11 @@ roi_pool_fwd_kernel(const float* __restrict__ feat, int C, int H, int W, const f
             for (int c = 0; c < CT; ++c) {
                 const float4* s4 = reinterpret_cast<const float4*>(src + (size_t)c * HW);
                 float4* d4 = reinterpret_cast<float4*>(planes + c * plane_stride);
-                for (int i = threadIdx.x; i < n4; i += kFwdThreads) d4[i] = __ldg(s4 + i);
+                for (int i = threadIdx.x; i < n4; i += NT) d4[i] = __ldg(s4 + i);
             }
         } else {
             for (int c = 0; c < CT; ++c)
-                for (int i = threadIdx.x; i < HW; i += kFwdThreads)
+                for (int i = threadIdx.x; i < HW; i += NT)
                     planes[c * plane_stride + i] = __ldg(src + (size_t)c * HW + i);
         }
     }
@@ -123,7 +127,7 @@ roi_pool_fwd_kernel(const float* __restrict__ feat, int C, int H, int W, const f
 
     const int r_begin = blockIdx.y * rois_per_cta;
     const int r_end = min(R, r_begin + rois_per_cta);
-    for (int r = r_begin + warp; r < r_end; r += kFwdWarps) {
+    for (int r = r_begin + warp; r < r_end; r += kWarps) {
         const RoiGeom g = roi_geometry(rois + (size_t)r * 5, scale, PH, PW);
         if (g.batch != b) continue;  // warp-uniform
         if (lane < PH) {
@@ -150,6 +154,8 @@ roi_pool_fwd_kernel(const float* __restrict__ feat, int C, int H, int W, const f
         }
         const int bwmax = (int)__reduce_max_sync(FULL_MASK, (unsigned)bw);
         const bool fast = bw >= 1 && bw >= bwmax - 1 && bwmax <= 16;
+        const float scl = (COMPACT && row_scale) ? __fadd_rn(row_scale[r], row_scale_bias) : 1.f;
+        uint32_t* sp = reinterpret_cast<uint32_t*>(sv);
         const bool shortlane = bw < bwmax;
         if (active) {
             for (int p = sub; p < npairs; p += nsub) {
@@ -190,12 +196,39 @@ roi_pool_fwd_kernel(const float* __restrict__ feat, int C, int H, int W, const f
                     outv = row[j];
                     idx = bh * W + ws + j;
                 }
-                sv[c * PP + ph * PW + pw] = outv;
-                si[c * PP + ph * PW + pw] = idx;
+                if (COMPACT) {
+                    const __nv_bfloat16 hv = __float2bfloat16_rn(__fmul_rn(outv, scl));
+                    sp[c * PP + ph * PW + pw] = ((uint32_t)__bfloat16_as_ushort(hv) << 16) | (uint32_t)(idx < 0 ? 0xFFFF : idx);
+                } else {
+                    sv[c * PP + ph * PW + pw] = outv;
+                    si[c * PP + ph * PW + pw] = idx;
+                }
             }
         }
         __syncwarp();
         const size_t obase = ((size_t)r * C + c0) * PP;
+        if (COMPACT) {
+            // n_out = CT*PP words -> two outputs per lane and store where the destination is 4-byte aligned
+            uint16_t* adst = argmax_u16 ? argmax_u16 + obase : nullptr;
+            uint16_t* vdst = out_bf16 ? reinterpret_cast<uint16_t*>(out_bf16 + (size_t)r * ld_bf16 + (size_t)c0 * PP) : nullptr;
+            const bool pair_ok = (n_out & 1) == 0 && (!adst || (reinterpret_cast<uintptr_t>(adst) & 3) == 0) &&
+                                 (!vdst || (reinterpret_cast<uintptr_t>(vdst) & 3) == 0);
+            if (pair_ok) {
+                for (int i = lane; i < (n_out >> 1); i += 32) {
+                    const uint32_t w0 = sp[2 * i], w1 = sp[2 * i + 1];
+                    if (adst) reinterpret_cast<uint32_t*>(adst)[i] = (w0 & 0xFFFFu) | (w1 << 16);
+                    if (vdst) reinterpret_cast<uint32_t*>(vdst)[i] = (w0 >> 16) | (w1 & 0xFFFF0000u);
+                }
+            } else {
+                for (int i = lane; i < n_out; i += 32) {
+                    const uint32_t w0 = sp[i];
+                    if (adst) adst[i] = (uint16_t)(w0 & 0xFFFFu);
+                    if (vdst) vdst[i] = (uint16_t)(w0 >> 16);
+                }
+            }
+            __syncwarp();
+            continue;
+        }
         if (out_f32)
             for (int i = lane; i < n_out; i += 32) out_f32[obase + i] = sv[i];
         if (argmax_i32)
@@ -391,7 +424,9 @@ roi_pool_bwd_kernel(const __grid_constant__ CUtensorMap tmap_arg, const __grid_c
         const int ea0 = warp * PP + (col0 - col_a);
         const int eg0 = warp * PP + (col0 - col_g);
         const unsigned lt_mask = (1u << lane) - 1u;
-        const int nent = RT * PP;
+        const int rr = lane & (RT - 1);          // RT is 8 or 16
+        const int BPS = 32 / RT;                 // bins per warp step
+        const int q = lane / RT;
         int st = 0;
         uint32_t phase = 0;
         for (int t = 0; t < ntiles; ++t) {
@@ -400,39 +435,42 @@ roi_pool_bwd_kernel(const __grid_constant__ CUtensorMap tmap_arg, const __grid_c
                 const uint8_t* ring = gen_base + ring_off + (size_t)st * (arg_stage + grad_stage);
                 const ArgT* ta = reinterpret_cast<const ArgT*>(ring);
                 const GradT* tg = reinterpret_cast<const GradT*>(ring + arg_stage);
-                const float2* smeta = s_meta + st * kBwdMaxRT;
-                // entry i = rr*PP + bin; (rr, bin) advance by 32 entries per step without divisions
-                int rr = lane / PP, bin = lane - rr * PP;
-                for (int i0 = 0; i0 < nent; i0 += 32) {
-                    int a = -1;
-                    float gval = 0.f;
-                    if (rr < RT) {
-                        const float2 meta = smeta[rr];
-                        const float sc = meta.x;
-                        if (meta.y != 0.f) {
-                            int ea = ea0 + bin, eg = eg0 + bin;
-                            int offa = rr * BW, offg = rr * BW;
-                            if (ea >= BW) { ea -= BW; offa += RT * BW; }
-                            if (eg >= BW) { eg -= BW; offg += RT * BW; }
-                            const ArgT raw = ta[offa + ea];
-                            int av;
-                            if (sizeof(ArgT) == 2)
-                                av = ((unsigned)raw == 0xFFFFu) ? -1 : (int)(unsigned)raw;
-                            else
-                                av = (int)raw;
-                            if (av >= band_lo && av < band_hi) {
-                                a = av - band_lo;
-                                float gv;
-                                if (sizeof(GradT) == 2)
-                                    gv = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(&tg[offg + eg]));
-                                else
-                                    gv = *reinterpret_cast<const float*>(&tg[offg + eg]);
-                                gval = gv * sc;
-                            }
-                        }
+                // Lane <-> (roi rr, bin slot q): a warp step covers RT rois x BPS consecutive bins, so the lanes of a
+                // step mostly belong to DIFFERENT rois and rarely collide on a cell (consecutive bins of one roi
+                // often share their arg-max cell); the next step's operands are fetched before this one resolves.
+                const float2 meta = s_meta[st * kBwdMaxRT + rr];
+                const bool ok = meta.y != 0.f;
+                const float sc = meta.x;
+                const int rowoff = rr * BW;
+                auto fetch = [&](int bin, int& av, float& gv) {
+                    av = -1;
+                    gv = 0.f;
+                    if (ok && bin < PP) {
+                        int ea = ea0 + bin, eg = eg0 + bin;
+                        int offa = rowoff, offg = rowoff;
+                        if (ea >= BW) { ea -= BW; offa += RT * BW; }
+                        if (eg >= BW) { eg -= BW; offg += RT * BW; }
+                        const ArgT raw = ta[offa + ea];
+                        if (sizeof(ArgT) == 2)
+                            av = ((unsigned)raw == 0xFFFFu) ? -1 : (int)(unsigned)raw;
+                        else
+                            av = (int)raw;
+                        if (sizeof(GradT) == 2)
+                            gv = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(&tg[offg + eg]));
+                        else
+                            gv = *reinterpret_cast<const float*>(&tg[offg + eg]);
                     }
-                    // lanes of this step that hit the same cell take turns in lane order (rank among their peers)
-                    const bool valid = a >= 0;
+                };
+                int av_n;
+                float gv_n;
+                fetch(q, av_n, gv_n);
+                for (int bin = q; bin - q < PP; bin += BPS) {
+                    const int av = av_n;
+                    const float gv = gv_n;
+                    fetch(bin + BPS, av_n, gv_n);
+                    const bool valid = av >= band_lo && av < band_hi;
+                    const int a = av - band_lo;
+                    const float gval = gv * sc;
                     const unsigned act = __ballot_sync(FULL_MASK, valid);
                     if (valid) {
                         const unsigned peers = __match_any_sync(act, a);
@@ -442,11 +480,6 @@ roi_pool_bwd_kernel(const __grid_constant__ CUtensorMap tmap_arg, const __grid_c
                             if (rank == k) my[a] += gval;
                             __syncwarp(act);
                         }
-                    }
-                    bin += 32;
-                    while (bin >= PP) {
-                        bin -= PP;
-                        ++rr;
                     }
                 }
             }
@@ -514,15 +547,16 @@ int device_max_smem() {
     return g_max_smem_optin > 0 ? g_max_smem_optin : 227 * 1024;
 }
 
-template <int CT>
+template <int CT, int NT, bool COMPACT>
 static int launch_fwd(const float* feat, int n, int c, int h, int w, const float* rois, int R, int PH, int PW,
                       float scale, const float* row_scale, float bias, float* out_f32, int32_t* a32, uint16_t* a16,
                       __nv_bfloat16* obf, long long ld, int plane_stride, size_t smem, cudaStream_t st) {
     const int groups = n * (c / CT);
+    constexpr int kWarps = NT / 32;
     // Split the ROIs into `chunks` CTAs per channel group so that groups*chunks fills a whole number of
     // waves of the SMs (1 CTA/SM: the planes take most of shared memory) with the smallest tail.
     const int sms = device_num_sms();
-    const int max_chunks = max(1, min(32, (R + kFwdWarps - 1) / kFwdWarps));
+    const int max_chunks = max(1, min(32, (R + kWarps - 1) / kWarps));
     int chunks = 1;
     double best = 1e30;
     for (int ch = 1; ch <= max_chunks; ++ch) {
@@ -535,11 +569,10 @@ static int launch_fwd(const float* feat, int n, int c, int h, int w, const float
     }
     const int rois_per_cta = (R + chunks - 1) / chunks;
     chunks = (R + rois_per_cta - 1) / rois_per_cta;
-    SOSWSOD_CHECK_CUDA(cudaFuncSetAttribute(roi_pool_fwd_kernel<CT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            (int)smem));
-    roi_pool_fwd_kernel<CT><<<dim3(groups, chunks), kFwdThreads, smem, st>>>(
-        feat, c, h, w, rois, R, PH, PW, scale, row_scale, bias, out_f32, a32, a16, obf, ld, plane_stride,
-        rois_per_cta);
+    auto kern = roi_pool_fwd_kernel<CT, NT, COMPACT>;
+    SOSWSOD_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<dim3(groups, chunks), NT, smem, st>>>(feat, c, h, w, rois, R, PH, PW, scale, row_scale, bias, out_f32, a32, a16,
+                                                 obf, ld, plane_stride, rois_per_cta);
     SOSWSOD_CHECK_LAUNCH();
     return SOSWSOD_OK;
 }
@@ -579,15 +612,26 @@ extern "C" int soswsod_roi_pool_forward(const float* feat, int n, int c, int h, 
         // channel c sits c*(32/nsub) banks away from channel 0, so the nsub sub-slots of a warp step hit different banks
         int plane_stride = ((HW + 31) / 32) * 32 + ((32 / nsub) % 32);
         if (CT == 1) plane_stride = ((HW + 3) / 4) * 4 + 4;   // >= 1 float of padding after the last row
-        const size_t smem = (size_t)CT * plane_stride * 4 + (size_t)kFwdWarps * CT * PP * 8 +
-                            (size_t)kFwdWarps * 4 * kFwdMaxP * 4;
+        const bool compact = !out_f32 && !a32;   // bf16 (+ uint16 argmax) outputs only: 32 warps, packed staging
+        const int warps = compact ? 32 : kFwdWarps;
+        const size_t smem = (size_t)CT * plane_stride * 4 + (size_t)warps * CT * PP * (compact ? 4 : 8) +
+                            (size_t)warps * 4 * kFwdMaxP * 4;
         if (smem > (size_t)max_smem) continue;
+#define SOSWSOD_FWD(CTV)                                                                                              \
+    case CTV:                                                                                                         \
+        return compact ? launch_fwd<CTV, 1024, true>(feat, n, c, h, w, rois, num_rois, pooled_h, pooled_w, spatial_scale, \
+                                                     row_scale, row_scale_bias, out_f32, a32, a16, obf, ld_bf16,          \
+                                                     plane_stride, smem, st)                                              \
+                       : launch_fwd<CTV, kFwdThreads, false>(feat, n, c, h, w, rois, num_rois, pooled_h, pooled_w,        \
+                                                             spatial_scale, row_scale, row_scale_bias, out_f32, a32, a16, \
+                                                             obf, ld_bf16, plane_stride, smem, st);
         switch (CT) {
-            case 8: return launch_fwd<8>(feat, n, c, h, w, rois, num_rois, pooled_h, pooled_w, spatial_scale, row_scale, row_scale_bias, out_f32, a32, a16, obf, ld_bf16, plane_stride, smem, st);
-            case 4: return launch_fwd<4>(feat, n, c, h, w, rois, num_rois, pooled_h, pooled_w, spatial_scale, row_scale, row_scale_bias, out_f32, a32, a16, obf, ld_bf16, plane_stride, smem, st);
-            case 2: return launch_fwd<2>(feat, n, c, h, w, rois, num_rois, pooled_h, pooled_w, spatial_scale, row_scale, row_scale_bias, out_f32, a32, a16, obf, ld_bf16, plane_stride, smem, st);
-            default: return launch_fwd<1>(feat, n, c, h, w, rois, num_rois, pooled_h, pooled_w, spatial_scale, row_scale, row_scale_bias, out_f32, a32, a16, obf, ld_bf16, plane_stride, smem, st);
+            SOSWSOD_FWD(8)
+            SOSWSOD_FWD(4)
+            SOSWSOD_FWD(2)
+            SOSWSOD_FWD(1)
         }
+#undef SOSWSOD_FWD
     }
     // plane larger than shared memory: global-memory kernel
     const long long warps = (long long)num_rois * c;
