@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define SOSWSOD_ABI_VERSION 1
+#define SOSWSOD_ABI_VERSION 2
 
 #define SOSWSOD_OK 0
 #define SOSWSOD_ERR_INVALID (-1)     /* bad shape / null pointer / misalignment */
@@ -63,12 +63,14 @@ int soswsod_roi_pool_forward(const float* feat, int n, int c, int h, int w, cons
 
 /* Atomic-free backward: grad_feat[n,c,h,w] (fully overwritten) = sum over (roi,bin) with
  * argmax == (h,w) of grad_out[roi, c*ph*pw + bin] * (row_scale[roi] + row_scale_bias).
- * grad_out is [num_rois, ld_grad] fp32 or bf16.  Replaces torchvision's atomicAdd backward
- * (same call sites as above). */
+ * grad_out is [num_rois, ld_grad] fp32 or bf16.  `argmax` must be the tensor soswsod_roi_pool_forward
+ * wrote for the same rois / spatial_scale (the kernel relies on arg-max cells lying inside their
+ * bins to schedule conflict-free updates).  Replaces torchvision's atomicAdd backward (same call
+ * sites as above). */
 int soswsod_roi_pool_backward(const void* grad_out, int grad_dtype, long long ld_grad, const void* argmax,
                               int argmax_dtype, const float* rois, int num_rois, const float* row_scale,
                               float row_scale_bias, int n, int c, int h, int w, int pooled_h, int pooled_w,
-                              float* grad_feat, soswsod_stream_t stream);
+                              float spatial_scale, float* grad_feat, soswsod_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * (2) fc6/fc7/head GEMMs on tcgen05 tensor cores, fp32 accumulation in TMEM, TMA-fed.

@@ -7,11 +7,10 @@
 // fp32 (bit-equal to torchvision), as argmax (int32 / uint16) and as the bf16 fc6 operand already
 // multiplied by (objectness + 1).
 //
-// Backward: a CTA owns ONE (image, channel) plane; each of its warps owns a private shared-memory copy
-// of the plane and a contiguous chunk of the ROIs.  Lanes take consecutive (roi, bin) entries; entries
-// of a warp step that hit the same cell are serialised by __match_any_sync rounds, so there is no
-// atomic anywhere and the summation order is fixed (deterministic).  The private planes are summed in
-// warp order and the result overwrites grad_feat.
+// Backward: a CTA owns the gradient planes of a few channels of one image in shared memory, one consumer
+// warp per plane (sole writer), fed by a TMA ring; a warp step takes the bins of one colour class of one
+// roi, which are pairwise disjoint, so there is no atomic and no conflict detection anywhere and the
+// summation order is fixed (deterministic).  See the comment above roi_pool_bwd_kernel.
 //
 // Bin arithmetic follows torchvision roi_pool exactly (restated in-repo by the reference at
 // uwsod/projects/WSL/wsl/layers/csrc/ROILoopPool/ROILoopPool_cuda.cu:77-137): C round() of the fp32
@@ -304,8 +303,15 @@ __global__ void roi_pool_fwd_global_kernel(const float* __restrict__ feat, int C
 // (roi, channel-group) tiles of argmax and grad_out through a TMA ring (cp.async.bulk.tensor + mbarriers): the
 // 98-byte per-channel runs of the [R, C*PH*PW] matrices are neither 16-byte aligned nor long enough for wide
 // loads; a TMA box only needs its first column 16-byte aligned, so each box starts at the aligned column at or
-// below the group's first entry and the consumers add the remainder.  Entries of one warp step that hit the
-// same cell are serialised by __match_any_sync rounds.
+// below the group's first entry and the consumers add the remainder.
+//
+// Conflict freedom inside a warp step comes from PROPOSAL-BIN OWNERSHIP instead of run-time conflict detection:
+// the arg-max of a bin lies inside the bin, and two bins of one roi can only share a cell when their row ranges
+// AND column ranges overlap.  The producer computes, per roi, the smallest strides (mh, mw) such that bins mh rows
+// (mw columns) apart are disjoint (2 x 2 for every roi at least 7 cells high and wide, larger for tiny rois whose
+// bins repeat cells); a warp step then takes the bins of ONE colour class (ph % mh, pw % mw) of one roi -- pairwise
+// disjoint by construction -- so every lane does a plain read-add-write on its own cell.  The argmax tensor must
+// therefore be the one soswsod_roi_pool_forward produced for the same rois (the autograd contract).
 constexpr int kBwdMaxCT = 8;
 constexpr int kBwdMaxRT = 16;  // rois per ring stage (8 or 16)
 
@@ -315,12 +321,32 @@ struct BwdCfg {
     size_t smem;
 };
 
-template <typename GradT, typename ArgT, int PPT>
+struct BwdRoiMeta {
+    float scale;   // row_scale[r] + bias
+    int code;      // 0 = skip this roi; else 1 | mh << 8 | mw << 16
+};
+
+// Smallest m >= 1 such that bin p and bin p + m (and anything further apart) never share a cell along one axis.
+__device__ __forceinline__ int bin_disjoint_stride(float bin, int rs, int P, int limit) {
+    int m = 1;
+    for (int p = 0; p + m < P; ++p) {
+        const int e = min(max((int)ceilf(__fmul_rn((float)(p + 1), bin)) + rs, 0), limit);
+        int q = p + m;
+        while (q < P && min(max((int)floorf(__fmul_rn((float)q, bin)) + rs, 0), limit) < e) ++q;
+        m = q - p;
+    }
+    return m;
+}
+
+template <typename GradT, typename ArgT, int PHT, int PWT>
 __global__ void __launch_bounds__((kBwdMaxCT + 1) * 32, 1)
 roi_pool_bwd_kernel(const __grid_constant__ CUtensorMap tmap_arg, const __grid_constant__ CUtensorMap tmap_grad,
                     const float* __restrict__ rois, int R, const float* __restrict__ row_scale, float row_scale_bias,
-                    int N, int C, int H, int W, int PP_rt, float* __restrict__ grad_feat, BwdCfg cfg) {
-    const int PP = PPT > 0 ? PPT : PP_rt;
+                    int N, int C, int H, int W, int PH_rt, int PW_rt, float spatial_scale,
+                    float* __restrict__ grad_feat, BwdCfg cfg) {
+    const int PH = PHT > 0 ? PHT : PH_rt;
+    const int PW = PWT > 0 ? PWT : PW_rt;
+    const int PP = PH * PW;
     extern __shared__ uint8_t smem_raw[];
     const int CT = cfg.CT, BW = cfg.BW, nbox = cfg.nbox, S = cfg.stages, RT = cfg.RT;
     const uint32_t base = (smem_u32(smem_raw) + 127u) & ~127u;
@@ -335,7 +361,7 @@ roi_pool_bwd_kernel(const __grid_constant__ CUtensorMap tmap_arg, const __grid_c
     auto full_bar = [&](int st) { return base + bar_off + 8u * st; };
     auto empty_bar = [&](int st) { return base + bar_off + 8u * (S + st); };
     int* s_range = reinterpret_cast<int*>(gen_base + bar_off + 16 * S);          // [2]
-    float2* s_meta = reinterpret_cast<float2*>(s_range + 2);                     // [S][kBwdMaxRT] = (scale, 1 | 0 = skip this roi)
+    BwdRoiMeta* s_meta = reinterpret_cast<BwdRoiMeta*>(s_range + 2);             // [S][kBwdMaxRT]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int groups = (C + CT - 1) / CT;
@@ -385,7 +411,7 @@ roi_pool_bwd_kernel(const __grid_constant__ CUtensorMap tmap_arg, const __grid_c
     const int col_g = col0 & ~(16 / (int)sizeof(GradT) - 1);
 
     if (warp == CT) {
-        // ---- producer warp: lane 0 drives the barriers and TMA, lanes < RT publish each roi's scale / skip flag ----
+        // ---- producer warp: lane 0 drives the barriers and TMA, lanes < RT publish each roi's scale and colouring ----
         uint32_t tx = 0;
         for (int bx = 0; bx < nbox; ++bx) {
             if (col_a + bx * BW < total_cols) tx += arg_box;
@@ -394,15 +420,26 @@ roi_pool_bwd_kernel(const __grid_constant__ CUtensorMap tmap_arg, const __grid_c
         int st = 0;
         uint32_t phase = 0;
         for (int t = 0; t < ntiles; ++t) {
-            mbar_wait(empty_bar(st), phase ^ 1u);
             const int r0 = r_lo + t * RT;
+            // the roi geometry does not depend on the ring slot: compute it before waiting for the slot
+            BwdRoiMeta meta;
+            meta.scale = 0.f;
+            meta.code = 0;
             if (lane < RT) {
                 const int r = r0 + lane;
-                float2 meta = make_float2(0.f, 0.f);
-                if (r < r_hi && (N == 1 || (int)rois[(size_t)r * 5] == b))
-                    meta = make_float2(row_scale ? __fadd_rn(row_scale[r], row_scale_bias) : 1.f, 1.f);
-                s_meta[st * kBwdMaxRT + lane] = meta;
+                if (r < r_hi && (N == 1 || (int)rois[(size_t)r * 5] == b)) {
+                    const RoiGeom g = roi_geometry(rois + (size_t)r * 5, spatial_scale, PH, PW);
+                    int mh = bin_disjoint_stride(g.bin_h, g.rs_h, PH, H);
+                    int mw = bin_disjoint_stride(g.bin_w, g.rs_w, PW, W);
+                    while (((PH + mh - 1) / mh) * ((PW + mw - 1) / mw) > 32) {   // one colour class per warp step
+                        if (mh <= mw) ++mh; else ++mw;
+                    }
+                    meta.scale = row_scale ? __fadd_rn(row_scale[r], row_scale_bias) : 1.f;
+                    meta.code = 1 | (mh << 8) | (mw << 16);
+                }
             }
+            mbar_wait(empty_bar(st), phase ^ 1u);
+            if (lane < RT) s_meta[st * kBwdMaxRT + lane] = meta;
             __syncwarp();
             if (lane == 0) {
                 mbar_expect_tx(full_bar(st), tx);
@@ -423,10 +460,6 @@ roi_pool_bwd_kernel(const __grid_constant__ CUtensorMap tmap_arg, const __grid_c
         const bool chan_ok = (c0 + warp) < C;
         const int ea0 = warp * PP + (col0 - col_a);
         const int eg0 = warp * PP + (col0 - col_g);
-        const unsigned lt_mask = (1u << lane) - 1u;
-        const int rr = lane & (RT - 1);          // RT is 8 or 16
-        const int BPS = 32 / RT;                 // bins per warp step
-        const int q = lane / RT;
         int st = 0;
         uint32_t phase = 0;
         for (int t = 0; t < ntiles; ++t) {
@@ -435,51 +468,46 @@ roi_pool_bwd_kernel(const __grid_constant__ CUtensorMap tmap_arg, const __grid_c
                 const uint8_t* ring = gen_base + ring_off + (size_t)st * (arg_stage + grad_stage);
                 const ArgT* ta = reinterpret_cast<const ArgT*>(ring);
                 const GradT* tg = reinterpret_cast<const GradT*>(ring + arg_stage);
-                // Lane <-> (roi rr, bin slot q): a warp step covers RT rois x BPS consecutive bins, so the lanes of a
-                // step mostly belong to DIFFERENT rois and rarely collide on a cell (consecutive bins of one roi
-                // often share their arg-max cell); the next step's operands are fetched before this one resolves.
-                const float2 meta = s_meta[st * kBwdMaxRT + rr];
-                const bool ok = meta.y != 0.f;
-                const float sc = meta.x;
-                const int rowoff = rr * BW;
-                auto fetch = [&](int bin, int& av, float& gv) {
-                    av = -1;
-                    gv = 0.f;
-                    if (ok && bin < PP) {
-                        int ea = ea0 + bin, eg = eg0 + bin;
-                        int offa = rowoff, offg = rowoff;
-                        if (ea >= BW) { ea -= BW; offa += RT * BW; }
-                        if (eg >= BW) { eg -= BW; offg += RT * BW; }
-                        const ArgT raw = ta[offa + ea];
-                        if (sizeof(ArgT) == 2)
-                            av = ((unsigned)raw == 0xFFFFu) ? -1 : (int)(unsigned)raw;
-                        else
-                            av = (int)raw;
-                        if (sizeof(GradT) == 2)
-                            gv = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(&tg[offg + eg]));
-                        else
-                            gv = *reinterpret_cast<const float*>(&tg[offg + eg]);
-                    }
-                };
-                int av_n;
-                float gv_n;
-                fetch(q, av_n, gv_n);
-                for (int bin = q; bin - q < PP; bin += BPS) {
-                    const int av = av_n;
-                    const float gv = gv_n;
-                    fetch(bin + BPS, av_n, gv_n);
-                    const bool valid = av >= band_lo && av < band_hi;
-                    const int a = av - band_lo;
-                    const float gval = gv * sc;
-                    const unsigned act = __ballot_sync(FULL_MASK, valid);
-                    if (valid) {
-                        const unsigned peers = __match_any_sync(act, a);
-                        const unsigned rank = __popc(peers & lt_mask);
-                        const unsigned rounds = __reduce_max_sync(act, rank);
-                        for (unsigned k = 0; k <= rounds; ++k) {
-                            if (rank == k) my[a] += gval;
-                            __syncwarp(act);
+                for (int rr = 0; rr < RT; ++rr) {
+                    const BwdRoiMeta meta = s_meta[st * kBwdMaxRT + rr];   // warp-uniform
+                    if (meta.code == 0) continue;
+                    const int mh = (meta.code >> 8) & 0xFF, mw = (meta.code >> 16) & 0xFF;
+                    const int nsteps = mh * mw;
+                    const int rowoff = rr * BW;
+                    // operands of colour step s for this lane: bin (i + a*mh, j + b*mw), (i, j) = (s / mw, s % mw)
+                    auto fetch = [&](int s, int& av, float& gv) {
+                        av = -1;
+                        gv = 0.f;
+                        const int i = s / mw, j = s - i * mw;
+                        const int nB = (PW - j + mw - 1) / mw;
+                        const int nA = (PH - i + mh - 1) / mh;
+                        if (lane < nA * nB) {
+                            const int a = lane / nB, bb = lane - a * nB;
+                            const int bin = (i + a * mh) * PW + j + bb * mw;
+                            int ea = ea0 + bin, eg = eg0 + bin;
+                            int offa = rowoff, offg = rowoff;
+                            if (ea >= BW) { ea -= BW; offa += RT * BW; }
+                            if (eg >= BW) { eg -= BW; offg += RT * BW; }
+                            const ArgT raw = ta[offa + ea];
+                            if (sizeof(ArgT) == 2)
+                                av = ((unsigned)raw == 0xFFFFu) ? -1 : (int)(unsigned)raw;
+                            else
+                                av = (int)raw;
+                            if (sizeof(GradT) == 2)
+                                gv = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(&tg[offg + eg]));
+                            else
+                                gv = *reinterpret_cast<const float*>(&tg[offg + eg]);
                         }
+                    };
+                    int av_n;
+                    float gv_n;
+                    fetch(0, av_n, gv_n);
+                    for (int s = 0; s < nsteps; ++s) {
+                        const int av = av_n;
+                        const float gv = gv_n;
+                        if (s + 1 < nsteps) fetch(s + 1, av_n, gv_n);
+                        if (av >= band_lo && av < band_hi) my[av - band_lo] += gv * meta.scale;
+                        __syncwarp();   // colour classes of one roi may share cells: order the steps
                     }
                 }
             }
@@ -693,9 +721,10 @@ static bool pick_bwd_cfg(int n, int c, int h, int w, int PP, int arg_bytes, int 
 
 template <typename GradT, typename ArgT>
 static int launch_bwd(const void* grad, long long ld_grad, const void* argmax, const float* rois, int R,
-                      const float* row_scale, float bias, int n, int c, int h, int w, int PP, float* grad_feat,
-                      cudaStream_t st) {
+                      const float* row_scale, float bias, int n, int c, int h, int w, int PH, int PW, float scale,
+                      float* grad_feat, cudaStream_t st) {
     const int HW = h * w;
+    const int PP = PH * PW;
     BwdCfg cfg;
     const bool aligned = ((uintptr_t)grad & 15) == 0 && ((uintptr_t)argmax & 15) == 0 &&
                          ((ld_grad * (long long)sizeof(GradT)) & 15) == 0 && (((long long)c * PP * sizeof(ArgT)) & 15) == 0;
@@ -710,14 +739,14 @@ static int launch_bwd(const void* grad, long long ld_grad, const void* argmax, c
         if (rc) return rc;
         const int grid = n * ((c + cfg.CT - 1) / cfg.CT) * cfg.bands;
         const int threads = (cfg.CT + 1) * 32;
-        if (PP == 49) {
-            auto kern = roi_pool_bwd_kernel<GradT, ArgT, 49>;
+        if (PH == 7 && PW == 7) {
+            auto kern = roi_pool_bwd_kernel<GradT, ArgT, 7, 7>;
             SOSWSOD_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem));
-            kern<<<grid, threads, cfg.smem, st>>>(ta, tg, rois, R, row_scale, bias, n, c, h, w, PP, grad_feat, cfg);
+            kern<<<grid, threads, cfg.smem, st>>>(ta, tg, rois, R, row_scale, bias, n, c, h, w, PH, PW, scale, grad_feat, cfg);
         } else {
-            auto kern = roi_pool_bwd_kernel<GradT, ArgT, 0>;
+            auto kern = roi_pool_bwd_kernel<GradT, ArgT, 0, 0>;
             SOSWSOD_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem));
-            kern<<<grid, threads, cfg.smem, st>>>(ta, tg, rois, R, row_scale, bias, n, c, h, w, PP, grad_feat, cfg);
+            kern<<<grid, threads, cfg.smem, st>>>(ta, tg, rois, R, row_scale, bias, n, c, h, w, PH, PW, scale, grad_feat, cfg);
         }
         SOSWSOD_CHECK_LAUNCH();
         return SOSWSOD_OK;
@@ -735,7 +764,8 @@ static int launch_bwd(const void* grad, long long ld_grad, const void* argmax, c
 extern "C" int soswsod_roi_pool_backward(const void* grad_out, int grad_dtype, long long ld_grad,
                                          const void* argmax, int argmax_dtype, const float* rois, int num_rois,
                                          const float* row_scale, float row_scale_bias, int n, int c, int h, int w,
-                                         int pooled_h, int pooled_w, float* grad_feat, soswsod_stream_t stream) {
+                                         int pooled_h, int pooled_w, float spatial_scale, float* grad_feat,
+                                         soswsod_stream_t stream) {
     SOSWSOD_CHECK_ARG(grad_out && argmax && rois && grad_feat, "roi_pool_backward: null pointer");
     SOSWSOD_CHECK_ARG(n > 0 && c > 0 && h > 0 && w > 0 && num_rois >= 0, "roi_pool_backward: bad shape");
     SOSWSOD_CHECK_ARG(grad_dtype == SOSWSOD_DTYPE_F32 || grad_dtype == SOSWSOD_DTYPE_BF16, "roi_pool_backward: bad grad dtype");
@@ -745,10 +775,10 @@ extern "C" int soswsod_roi_pool_backward(const void* grad_out, int grad_dtype, l
     cudaStream_t st = (cudaStream_t)stream;
     if (grad_dtype == SOSWSOD_DTYPE_F32) {
         if (argmax_dtype == SOSWSOD_ARGMAX_I32)
-            return launch_bwd<float, int32_t>(grad_out, ld_grad, argmax, rois, num_rois, row_scale, row_scale_bias, n, c, h, w, PP, grad_feat, st);
-        return launch_bwd<float, uint16_t>(grad_out, ld_grad, argmax, rois, num_rois, row_scale, row_scale_bias, n, c, h, w, PP, grad_feat, st);
+            return launch_bwd<float, int32_t>(grad_out, ld_grad, argmax, rois, num_rois, row_scale, row_scale_bias, n, c, h, w, pooled_h, pooled_w, spatial_scale, grad_feat, st);
+        return launch_bwd<float, uint16_t>(grad_out, ld_grad, argmax, rois, num_rois, row_scale, row_scale_bias, n, c, h, w, pooled_h, pooled_w, spatial_scale, grad_feat, st);
     }
     if (argmax_dtype == SOSWSOD_ARGMAX_I32)
-        return launch_bwd<__nv_bfloat16, int32_t>(grad_out, ld_grad, argmax, rois, num_rois, row_scale, row_scale_bias, n, c, h, w, PP, grad_feat, st);
-    return launch_bwd<__nv_bfloat16, uint16_t>(grad_out, ld_grad, argmax, rois, num_rois, row_scale, row_scale_bias, n, c, h, w, PP, grad_feat, st);
+        return launch_bwd<__nv_bfloat16, int32_t>(grad_out, ld_grad, argmax, rois, num_rois, row_scale, row_scale_bias, n, c, h, w, pooled_h, pooled_w, spatial_scale, grad_feat, st);
+    return launch_bwd<__nv_bfloat16, uint16_t>(grad_out, ld_grad, argmax, rois, num_rois, row_scale, row_scale_bias, n, c, h, w, pooled_h, pooled_w, spatial_scale, grad_feat, st);
 }

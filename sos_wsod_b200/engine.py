@@ -247,7 +247,8 @@ class OICRPlusHeadEngine:
             for f, r, am in zip(vb.feats, vb.rois, argmaxes):
                 m = r.size(0)
                 grad_feats.append(ops.roi_pool_backward(dX[row:row + m], am, r, tuple(f.shape), (cfg.pooled, cfg.pooled),
-                                                        row_scale=vb.obj[row:row + m], row_scale_bias=1.0))
+                                                        row_scale=vb.obj[row:row + m], row_scale_bias=1.0,
+                                                        spatial_scale=cfg.spatial_scale))
                 row += m
                 self.launches_last_step += 1
         grads = {"fc1_w": dW6, "fc1_b": db6, "fc2_w": dW7, "fc2_b": db7}

@@ -27,7 +27,7 @@ class _ROIPool(Function):
     def backward(ctx, grad_output):
         rois, argmax = ctx.saved_tensors
         grad_input = ops.roi_pool_backward(grad_output.contiguous().float(), argmax, rois, tuple(ctx.input_shape),
-                                           ctx.output_size)
+                                           ctx.output_size, spatial_scale=ctx.spatial_scale)
         return grad_input, None, None, None
 
 

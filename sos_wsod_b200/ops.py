@@ -81,8 +81,9 @@ def roi_pool_forward(feat: torch.Tensor, rois: torch.Tensor, pooled: Tuple[int, 
 
 def roi_pool_backward(grad_out: torch.Tensor, argmax: torch.Tensor, rois: torch.Tensor, feat_shape,
                       pooled: Tuple[int, int] = (7, 7), row_scale: Optional[torch.Tensor] = None,
-                      row_scale_bias: float = 0.0) -> torch.Tensor:
-    """grad_out [M, C*ph*pw] (or [M,C,ph,pw]) fp32/bf16 -> grad_feat fp32 [N,C,H,W] (overwritten, atomic-free)."""
+                      row_scale_bias: float = 0.0, spatial_scale: float = 0.125) -> torch.Tensor:
+    """grad_out [M, C*ph*pw] (or [M,C,ph,pw]) fp32/bf16 -> grad_feat fp32 [N,C,H,W] (overwritten, atomic-free).
+    `argmax` must come from roi_pool_forward on the same rois and spatial_scale."""
     _need_cuda(grad_out, argmax, rois)
     n, c, h, w = feat_shape
     ph, pw = pooled
@@ -101,7 +102,7 @@ def roi_pool_backward(grad_out: torch.Tensor, argmax: torch.Tensor, rois: torch.
     lib = _lib.load()
     check(lib.soswsod_roi_pool_backward(_ptr(grad_out), _dt(grad_out), grad_out.stride(0), _ptr(argmax.contiguous()), a_dt,
                                         _ptr(rois), m, _ptr(row_scale), float(row_scale_bias), n, c, h, w, ph, pw,
-                                        _ptr(grad_feat), _stream()), "roi_pool_backward")
+                                        float(spatial_scale), _ptr(grad_feat), _stream()), "roi_pool_backward")
     _count(1)
     return grad_feat
 

@@ -143,6 +143,34 @@ def test_roi_pool_backward_plane_configs(ops, C, h, w, N):
     torch.testing.assert_close(gf.cpu(), feat.grad, rtol=1e-4, atol=1e-4)
 
 
+@pytest.mark.parametrize("pooled", [(7, 7), (3, 5), (2, 2), (6, 9)])
+def test_roi_pool_backward_tiny_rois(ops, pooled):
+    """rois only 1..6 cells high / wide repeat cells across many bins (the colour strides of the bin-ownership
+    schedule grow beyond 2), all-zero features make every bin of a roi row-major-first ties, and pooled grids
+    other than 7x7 take the generic template."""
+    import torchvision
+
+    g = _gen(77 + pooled[0])
+    C, h, w, R = 16, 40, 50, 300
+    feat = torch.relu(torch.randn((1, C, h, w), generator=g))
+    feat[:, :4] = 0.0
+    feat.requires_grad_(True)
+    x1 = torch.rand(R, generator=g) * (w * 8 - 60)
+    y1 = torch.rand(R, generator=g) * (h * 8 - 60)
+    bw = torch.rand(R, generator=g) * 56 + 1
+    bh = torch.rand(R, generator=g) * 56 + 1
+    bw[::3] = torch.rand(R, generator=g)[::3] * 200 + 1
+    boxes = torch.stack([x1, y1, x1 + bw, y1 + bh], 1).round()
+    rois = ref.boxes_to_pooler_format([boxes])
+    pooled_ref = torchvision.ops.roi_pool(feat, rois, pooled, 0.125)
+    go = torch.randn(pooled_ref.shape, generator=g)
+    pooled_ref.backward(go)
+    out, arg, _ = ops.roi_pool_forward(feat.detach().cuda(), rois.cuda(), pooled)
+    assert torch.equal(out.cpu(), pooled_ref.detach())
+    gf = ops.roi_pool_backward(go.flatten(1).cuda(), arg, rois.cuda(), (1, C, h, w), pooled)
+    torch.testing.assert_close(gf.cpu(), feat.grad, rtol=1e-4, atol=1e-4)
+
+
 # ------------------------------------------------------------------------------------------------
 # (2) GEMM
 # ------------------------------------------------------------------------------------------------
