@@ -431,9 +431,10 @@ roi_pool_bwd_kernel(const __grid_constant__ CUtensorMap tmap_arg, const __grid_c
                     const RoiGeom g = roi_geometry(rois + (size_t)r * 5, spatial_scale, PH, PW);
                     int mh = bin_disjoint_stride(g.bin_h, g.rs_h, PH, H);
                     int mw = bin_disjoint_stride(g.bin_w, g.rs_w, PW, W);
-                    while (((PH + mh - 1) / mh) * ((PW + mw - 1) / mw) > 32) {   // one colour class per warp step
-                        if (mh <= mw) ++mh; else ++mw;
-                    }
+                    // a colour class must fit the 4 x 8 lane grid of a warp step
+                    // (and strides of at least 2 keep the number of unrolled variants small)
+                    mh = max(max(mh, 2), (PH + 3) / 4);
+                    mw = max(max(mw, 2), (PW + 7) / 8);
                     meta.scale = row_scale ? __fadd_rn(row_scale[r], row_scale_bias) : 1.f;
                     meta.code = 1 | (mh << 8) | (mw << 16);
                 }
@@ -456,58 +457,135 @@ roi_pool_bwd_kernel(const __grid_constant__ CUtensorMap tmap_arg, const __grid_c
             }
         }
     } else if (warp < CT) {
-        float* my = planes + warp * cfg.plane_stride;
+        // this warp's plane as a shared-window address held in a register (opaque to the compiler, which otherwise
+        // re-derives it from the kernel parameters inside the dependent read-add-write chain)
+        uint32_t my_s = smem_u32(planes + warp * cfg.plane_stride);
+        asm volatile("mov.u32 %0, %0;" : "+r"(my_s));
         const bool chan_ok = (c0 + warp) < C;
         const int ea0 = warp * PP + (col0 - col_a);
         const int eg0 = warp * PP + (col0 - col_g);
+        const unsigned band_cells = (unsigned)(band_hi - band_lo);
+        // Lane = (la, lb) = (lane >> 3, lane & 7) owns the block of mh x mw bins at (la*mh, lb*mw); colour step (i, j)
+        // touches bin (la*mh + i, lb*mw + j) of every block.
+        const int la = lane >> 3, lb = lane & 7;
+        // byte offset, inside a ring stage, of this warp's entry `bin` of the roi in slot 0
+        auto off_arg = [&](int bin) {
+            int e = ea0 + bin, o = 0;
+            if (e >= BW) { e -= BW; o = RT * BW; }
+            return (o + e) * (int)sizeof(ArgT);
+        };
+        auto off_grad = [&](int bin) {
+            int e = eg0 + bin, o = 0;
+            if (e >= BW) { e -= BW; o = RT * BW; }
+            return (o + e) * (int)sizeof(GradT);
+        };
+        // strides 2 x 2 (every roi at least PH x PW cells, the common case): the four operands of a lane sit at
+        // offsets that never change, so they are computed once
+        constexpr int kCode22 = 1 | (2 << 8) | (2 << 16);
+        int oa2[4], og2[4];
+        bool v2[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int ph = 2 * la + (k >> 1), pw = 2 * lb + (k & 1);
+            v2[k] = ph < PH && pw < PW;
+            oa2[k] = v2[k] ? off_arg(ph * PW + pw) : 0;
+            og2[k] = v2[k] ? off_grad(ph * PW + pw) : 0;
+        }
+        int row_a = BW * (int)sizeof(ArgT), row_g = BW * (int)sizeof(GradT), rt = RT;
+        asm volatile("mov.u32 %0, %0;" : "+r"(row_a));   // keep these in registers (see my_s)
+        asm volatile("mov.u32 %0, %0;" : "+r"(row_g));
+        asm volatile("mov.u32 %0, %0;" : "+r"(rt));
         int st = 0;
         uint32_t phase = 0;
         for (int t = 0; t < ntiles; ++t) {
             mbar_wait(full_bar(st), phase);
             if (chan_ok) {
-                const uint8_t* ring = gen_base + ring_off + (size_t)st * (arg_stage + grad_stage);
-                const ArgT* ta = reinterpret_cast<const ArgT*>(ring);
-                const GradT* tg = reinterpret_cast<const GradT*>(ring + arg_stage);
-                for (int rr = 0; rr < RT; ++rr) {
-                    const BwdRoiMeta meta = s_meta[st * kBwdMaxRT + rr];   // warp-uniform
-                    if (meta.code == 0) continue;
-                    const int mh = (meta.code >> 8) & 0xFF, mw = (meta.code >> 16) & 0xFF;
-                    const int nsteps = mh * mw;
-                    const int rowoff = rr * BW;
-                    // operands of colour step s for this lane: bin (i + a*mh, j + b*mw), (i, j) = (s / mw, s % mw)
-                    auto fetch = [&](int s, int& av, float& gv) {
-                        av = -1;
-                        gv = 0.f;
-                        const int i = s / mw, j = s - i * mw;
-                        const int nB = (PW - j + mw - 1) / mw;
-                        const int nA = (PH - i + mh - 1) / mh;
-                        if (lane < nA * nB) {
-                            const int a = lane / nB, bb = lane - a * nB;
-                            const int bin = (i + a * mh) * PW + j + bb * mw;
-                            int ea = ea0 + bin, eg = eg0 + bin;
-                            int offa = rowoff, offg = rowoff;
-                            if (ea >= BW) { ea -= BW; offa += RT * BW; }
-                            if (eg >= BW) { eg -= BW; offg += RT * BW; }
-                            const ArgT raw = ta[offa + ea];
-                            if (sizeof(ArgT) == 2)
-                                av = ((unsigned)raw == 0xFFFFu) ? -1 : (int)(unsigned)raw;
-                            else
-                                av = (int)raw;
-                            if (sizeof(GradT) == 2)
-                                gv = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(&tg[offg + eg]));
-                            else
-                                gv = *reinterpret_cast<const float*>(&tg[offg + eg]);
+                const uint8_t* pa = gen_base + ring_off + (size_t)st * (arg_stage + grad_stage);
+                const uint8_t* pg = pa + arg_stage;
+                const BwdRoiMeta* metas = s_meta + st * kBwdMaxRT;
+                auto ld_arg = [&](int off) -> unsigned {
+                    if (sizeof(ArgT) == 2) return (unsigned)*reinterpret_cast<const uint16_t*>(pa + off);
+                    return *reinterpret_cast<const unsigned*>(pa + off);
+                };
+                auto ld_grad = [&](int off) -> float {
+                    if (sizeof(GradT) == 2)
+                        return __uint_as_float((unsigned)*reinterpret_cast<const uint16_t*>(pg + off) << 16);
+                    return *reinterpret_cast<const float*>(pg + off);
+                };
+                // one colour step: plain read-add-write, lanes of a step never share a cell.  An empty bin (0xFFFF /
+                // -1), an idle lane (0xFFFFFFFF) and a cell outside this CTA's row band all fail the range test.
+                auto rmw = [&](unsigned a, float g) {
+                    const unsigned rel = a - (unsigned)band_lo;
+                    if (rel < band_cells) {
+                        const uint32_t addr = my_s + rel * 4u;
+                        float v;
+                        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+                        v += g;
+                        asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+                    }
+                    __syncwarp();   // colour classes of one roi may share cells: order the steps
+                };
+                // The tile is consumed as GROUPS of up to four colour steps: the operands of group g+1 are fetched
+                // (8 independent loads) before the four ordered read-add-write steps of group g run, so the only
+                // dependent chain left is the one on the plane.  A 2 x 2 roi is exactly one group; rois with larger
+                // strides take several; a skipped roi (code 0) is an empty group.  (nrr, ni, nj) = next step to fetch.
+                int nrr = 0, ni = 0, nj = 0;
+                BwdRoiMeta m0 = metas[0];                                           // meta of roi nrr
+                BwdRoiMeta m1 = metas[1];                                           // meta of roi nrr + 1 (RT >= 8)
+                auto next_roi = [&]() {
+                    ++nrr;
+                    ni = nj = 0;
+                    m0 = m1;
+                    m1.code = 0;
+                    if (nrr + 1 < rt) m1 = metas[nrr + 1];   // used one group later at the earliest
+                };
+                auto fetch_group = [&](unsigned (&a)[4], float (&g)[4]) {
+                    const float sc = m0.scale;
+                    if (m0.code == kCode22) {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            a[k] = 0xFFFFFFFFu;
+                            g[k] = 0.f;
+                            if (v2[k]) {
+                                a[k] = ld_arg(nrr * row_a + oa2[k]);
+                                g[k] = ld_grad(nrr * row_g + og2[k]) * sc;
+                            }
                         }
-                    };
-                    int av_n;
-                    float gv_n;
-                    fetch(0, av_n, gv_n);
-                    for (int s = 0; s < nsteps; ++s) {
-                        const int av = av_n;
-                        const float gv = gv_n;
-                        if (s + 1 < nsteps) fetch(s + 1, av_n, gv_n);
-                        if (av >= band_lo && av < band_hi) my[av - band_lo] += gv * meta.scale;
-                        __syncwarp();   // colour classes of one roi may share cells: order the steps
+                        next_roi();
+                        return;
+                    }
+                    const int mh = (m0.code >> 8) & 0xFF, mw = (m0.code >> 16) & 0xFF;   // 0 for a skipped roi
+                    const int ph0 = la * mh, pw0 = lb * mw;
+                    const int ra = nrr * row_a, rg = nrr * row_g;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        a[k] = 0xFFFFFFFFu;
+                        g[k] = 0.f;
+                        const int ph = ph0 + ni, pw = pw0 + nj;
+                        if (ni < mh && ph < PH && pw < PW) {
+                            a[k] = ld_arg(ra + off_arg(ph * PW + pw));
+                            g[k] = ld_grad(rg + off_grad(ph * PW + pw)) * sc;
+                        }
+                        if (++nj >= mw) {
+                            nj = 0;
+                            ++ni;
+                        }
+                    }
+                    if (ni >= mh) next_roi();
+                };
+                unsigned ca[4], na[4];
+                float cg[4], ng[4];
+                fetch_group(ca, cg);
+                while (true) {
+                    const bool more = nrr < rt;
+                    if (more) fetch_group(na, ng);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) rmw(ca[k], cg[k]);
+                    if (!more) break;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        ca[k] = na[k];
+                        cg[k] = ng[k];
                     }
                 }
             }
