@@ -96,7 +96,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
@@ -109,7 +109,7 @@ class ClockSampler:
 
     def wait_first_sample(self, timeout=15.0):
         """nvidia-smi takes a second or two to attach to the driver (and slows CUDA calls while it does): the
-        timed region only starts once it is in its steady 200 ms polling loop."""
+        timed region only starts once it is in its steady 100 ms polling loop."""
         t0 = time.perf_counter()
         while self.proc is not None and not self.lines and time.perf_counter() - t0 < timeout:
             time.sleep(0.05)
@@ -349,9 +349,22 @@ def run_b200_arm(args):
     fc6 = max(detail, key=lambda d: d["m"] * d["n"] * d["k"] if not d["a_mn"] and not d["b_mn"] else 0)
     achieved = tot_flops / tot_ms / 1e9 if tot_ms > 0 else 0.0
     peak = peaks["bf16_tflops_sustained"]
-    roofline = {"bound": "tensor", "kernel": "gemm_bf16_kernel (tcgen05, all 10 launches of a step)", "achieved": achieved,
+    n_gemm = len(gemm_events) // max(args.steps, 1)
+    # DRAM traffic of the same launches from the committed `ncu --set full` capture (profiles/ncu_traffic.json);
+    # averaged per launch like `achieved`.  Algorithmic bytes = operands read once + output written once.
+    traffic, traffic_src = None, None
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            tj = json.load(f)
+        traffic = tj["gemm_bf16_kernel"]["dram_bytes_per_launch_avg"]
+        traffic_src = tj["source"]
+    alg_bytes = sum(2.0 * (s[0] * s[2] + s[1] * s[2]) + 2.0 * s[0] * s[1] for s in by_shape) / max(len(by_shape), 1)
+    roofline = {"bound": "tensor", "kernel": f"gemm_bf16_kernel (tcgen05, all {n_gemm} launches of a step)", "achieved": achieved,
                 "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "peak_source": peaks["source"] + ", sustained",
-                "traffic": None, "gemm_share_of_step": tot_ms / ms, "fc6_fwd_tflops": fc6["tflops"], "detail": detail}
+                "traffic": traffic, "traffic_unit": "DRAM bytes per launch (avg over the step's GEMM launches)",
+                "traffic_source": traffic_src, "algorithmic_bytes_per_launch": alg_bytes,
+                "gemm_share_of_step": tot_ms / ms, "fc6_fwd_tflops": fc6["tflops"], "detail": detail}
 
     # ---- end to end through the plugin surface, host buffers, H2D/D2H inside the timed region ----
     heads.grad_hook = grad_hook
@@ -433,7 +446,7 @@ def run_b200_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
