@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define SOSWSOD_ABI_VERSION 2
+#define SOSWSOD_ABI_VERSION 3
 
 #define SOSWSOD_OK 0
 #define SOSWSOD_ERR_INVALID (-1)     /* bad shape / null pointer / misalignment */
@@ -55,11 +55,24 @@ const char* soswsod_last_error(void);
  *              int32 or uint16 per `argmax_dtype` (may be NULL)
  *   out_bf16   bf16 [num_rois, ld_bf16] = pooled * (row_scale[r] + row_scale_bias), the fc6 GEMM
  *              operand (may be NULL).  row_scale NULL => factor 1.
+ *   plan       optional (NULL allowed): the per-call plan written by soswsod_roi_pool_plan for the SAME
+ *              rois / n / h / w / spatial_scale / row_scale (7x7 bins only).  With a plan, uint16
+ *              arg-max and only out_bf16 requested (the head engine's operand mode) the forward runs
+ *              the channel-interleaved window-table kernel; the backward (bf16 or fp32 grad, uint16
+ *              arg-max) runs the two-planes-per-warp kernel.  Results are identical with and without.
  * ------------------------------------------------------------------------------------------- */
+/* Bytes of a plan for num_rois rois (0 when the pooled size has no plan). */
+size_t soswsod_roi_pool_plan_bytes(int num_rois, int pooled_h, int pooled_w);
+/* Groups the rois by image and stores every roi's bin bounds, scale factor and backward colouring
+ * (bin arithmetic of torchvision roi_pool, done once per roi).  plan: 128-byte aligned, n <= 64. */
+int soswsod_roi_pool_plan(const float* rois, int num_rois, int n, int h, int w, int pooled_h, int pooled_w,
+                          float spatial_scale, const float* row_scale, float row_scale_bias, void* plan,
+                          size_t plan_bytes, soswsod_stream_t stream);
 int soswsod_roi_pool_forward(const float* feat, int n, int c, int h, int w, const float* rois, int num_rois,
                              int pooled_h, int pooled_w, float spatial_scale, const float* row_scale,
                              float row_scale_bias, float* out_f32, void* argmax, int argmax_dtype,
-                             void* out_bf16, long long ld_bf16, soswsod_stream_t stream);
+                             void* out_bf16, long long ld_bf16, const void* plan, size_t plan_bytes,
+                             soswsod_stream_t stream);
 
 /* Atomic-free backward: grad_feat[n,c,h,w] (fully overwritten) = sum over (roi,bin) with
  * argmax == (h,w) of grad_out[roi, c*ph*pw + bin] * (row_scale[roi] + row_scale_bias).
@@ -70,7 +83,8 @@ int soswsod_roi_pool_forward(const float* feat, int n, int c, int h, int w, cons
 int soswsod_roi_pool_backward(const void* grad_out, int grad_dtype, long long ld_grad, const void* argmax,
                               int argmax_dtype, const float* rois, int num_rois, const float* row_scale,
                               float row_scale_bias, int n, int c, int h, int w, int pooled_h, int pooled_w,
-                              float spatial_scale, float* grad_feat, soswsod_stream_t stream);
+                              float spatial_scale, float* grad_feat, const void* plan, size_t plan_bytes,
+                              soswsod_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * (2) fc6/fc7/head GEMMs on tcgen05 tensor cores, fp32 accumulation in TMEM, TMA-fed.

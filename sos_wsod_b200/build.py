@@ -20,6 +20,7 @@ INCLUDE = os.path.join(os.path.dirname(_HERE), "include")
 SOURCES = [
     ("misc.cu", []),
     ("roi_pool.cu", ["-fmad=false"]),
+    ("roi_pool_fast.cu", ["-fmad=false"]),
     ("gemm.cu", []),
     ("wsddn.cu", []),
     ("oicr.cu", ["-fmad=false"]),
@@ -48,7 +49,7 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(LIB_DIR, exist_ok=True)
     obj_dir = os.path.join(LIB_DIR, "obj")
     os.makedirs(obj_dir, exist_ok=True)
-    headers = [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "tma.cuh"), os.path.join(INCLUDE, "soswsod_b200.h")]
+    headers = [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "tma.cuh"), os.path.join(CSRC, "roi_plan.cuh"), os.path.join(INCLUDE, "soswsod_b200.h")]
 
     def compile_one(item):
         src, extra = item

@@ -15,7 +15,7 @@
 // Bin arithmetic follows torchvision roi_pool exactly (restated in-repo by the reference at
 // uwsod/projects/WSL/wsl/layers/csrc/ROILoopPool/ROILoopPool_cuda.cu:77-137): C round() of the fp32
 // product, fp32 bin size, floor/ceil, clamp, strict '>' scan in row-major order, empty bin -> (0, -1).
-#include "common.cuh"
+#include "roi_plan.cuh"
 #include "tma.cuh"
 
 namespace soswsod {
@@ -23,25 +23,6 @@ namespace soswsod {
 constexpr int kFwdThreads = 512;
 constexpr int kFwdWarps = kFwdThreads / 32;
 constexpr int kMaxBins = 256;  // PH*PW limit
-
-struct RoiGeom {
-    int batch, rs_w, rs_h;
-    float bin_w, bin_h;
-};
-
-__device__ __forceinline__ RoiGeom roi_geometry(const float* __restrict__ roi, float scale, int PH, int PW) {
-    RoiGeom g;
-    g.batch = (int)roi[0];
-    g.rs_w = (int)roundf(__fmul_rn(roi[1], scale));
-    g.rs_h = (int)roundf(__fmul_rn(roi[2], scale));
-    const int re_w = (int)roundf(__fmul_rn(roi[3], scale));
-    const int re_h = (int)roundf(__fmul_rn(roi[4], scale));
-    const int roi_w = max(re_w - g.rs_w + 1, 1);
-    const int roi_h = max(re_h - g.rs_h + 1, 1);
-    g.bin_h = __fdiv_rn((float)roi_h, (float)PH);
-    g.bin_w = __fdiv_rn((float)roi_w, (float)PW);
-    return g;
-}
 
 // One bin column of BWM cells over rows [hs, he): running row maximum (strict '>' keeps the FIRST best row).
 // `row` points at (hs, ws).  A lane whose own range is one cell narrower (shortlane) masks the last load; that load
@@ -325,18 +306,6 @@ struct BwdRoiMeta {
     float scale;   // row_scale[r] + bias
     int code;      // 0 = skip this roi; else 1 | mh << 8 | mw << 16
 };
-
-// Smallest m >= 1 such that bin p and bin p + m (and anything further apart) never share a cell along one axis.
-__device__ __forceinline__ int bin_disjoint_stride(float bin, int rs, int P, int limit) {
-    int m = 1;
-    for (int p = 0; p + m < P; ++p) {
-        const int e = min(max((int)ceilf(__fmul_rn((float)(p + 1), bin)) + rs, 0), limit);
-        int q = p + m;
-        while (q < P && min(max((int)floorf(__fmul_rn((float)q, bin)) + rs, 0), limit) < e) ++q;
-        m = q - p;
-    }
-    return m;
-}
 
 template <typename GradT, typename ArgT, int PHT, int PWT>
 __global__ void __launch_bounds__((kBwdMaxCT + 1) * 32, 1)
@@ -691,7 +660,7 @@ extern "C" int soswsod_roi_pool_forward(const float* feat, int n, int c, int h, 
                                         int num_rois, int pooled_h, int pooled_w, float spatial_scale,
                                         const float* row_scale, float row_scale_bias, float* out_f32,
                                         void* argmax, int argmax_dtype, void* out_bf16, long long ld_bf16,
-                                        soswsod_stream_t stream) {
+                                        const void* plan, size_t plan_bytes, soswsod_stream_t stream) {
     SOSWSOD_CHECK_ARG(n > 0 && c > 0 && h > 0 && w > 0 && num_rois >= 0, "roi_pool_forward: bad shape");
     if (num_rois == 0) return SOSWSOD_OK;  // empty proposal list: nothing to write
     SOSWSOD_CHECK_ARG(feat && rois, "roi_pool_forward: null feat/rois");
@@ -709,6 +678,17 @@ extern "C" int soswsod_roi_pool_forward(const float* feat, int n, int c, int h, 
     const int PP = pooled_h * pooled_w;
     const int HW = h * w;
     const int max_smem = device_max_smem();
+    if (plan) {
+        SOSWSOD_CHECK_ARG(pooled_h == kPlanP && pooled_w == kPlanP, "roi_pool_forward: a plan is for 7x7 bins");
+        if (plan_bytes < plan_total_bytes(num_rois)) {
+            set_error("roi_pool_forward: plan of %zu bytes, need %zu", plan_bytes, plan_total_bytes(num_rois));
+            return SOSWSOD_ERR_WORKSPACE;
+        }
+        if (!out_f32 && !a32) {   // operand mode: channel-interleaved planes + row-window table
+            const int rc = launch_fwd_fast(feat, n, c, h, w, num_rois, plan, a16, obf, ld_bf16, st);
+            if (rc != 0) return rc < 0 ? rc : SOSWSOD_OK;
+        }
+    }
     // pick the largest channel group whose planes + staging fit
     const int cts[4] = {8, 4, 2, 1};
     for (int k = 0; k < 4 && pooled_h <= kFwdMaxP && pooled_w <= kFwdMaxP; ++k) {
@@ -843,7 +823,7 @@ extern "C" int soswsod_roi_pool_backward(const void* grad_out, int grad_dtype, l
                                          const void* argmax, int argmax_dtype, const float* rois, int num_rois,
                                          const float* row_scale, float row_scale_bias, int n, int c, int h, int w,
                                          int pooled_h, int pooled_w, float spatial_scale, float* grad_feat,
-                                         soswsod_stream_t stream) {
+                                         const void* plan, size_t plan_bytes, soswsod_stream_t stream) {
     SOSWSOD_CHECK_ARG(grad_out && argmax && rois && grad_feat, "roi_pool_backward: null pointer");
     SOSWSOD_CHECK_ARG(n > 0 && c > 0 && h > 0 && w > 0 && num_rois >= 0, "roi_pool_backward: bad shape");
     SOSWSOD_CHECK_ARG(grad_dtype == SOSWSOD_DTYPE_F32 || grad_dtype == SOSWSOD_DTYPE_BF16, "roi_pool_backward: bad grad dtype");
@@ -851,6 +831,18 @@ extern "C" int soswsod_roi_pool_backward(const void* grad_out, int grad_dtype, l
     const int PP = pooled_h * pooled_w;
     SOSWSOD_CHECK_ARG(ld_grad >= (long long)c * PP, "roi_pool_backward: ld_grad too small");
     cudaStream_t st = (cudaStream_t)stream;
+    if (plan && num_rois > 0) {
+        SOSWSOD_CHECK_ARG(pooled_h == kPlanP && pooled_w == kPlanP, "roi_pool_backward: a plan is for 7x7 bins");
+        if (plan_bytes < plan_total_bytes(num_rois)) {
+            set_error("roi_pool_backward: plan of %zu bytes, need %zu", plan_bytes, plan_total_bytes(num_rois));
+            return SOSWSOD_ERR_WORKSPACE;
+        }
+        if (argmax_dtype == SOSWSOD_ARGMAX_U16) {
+            const int rc = launch_bwd_fast(grad_out, grad_dtype, ld_grad, (const uint16_t*)argmax, num_rois, plan, n, c, h, w,
+                                           grad_feat, st);
+            if (rc != 0) return rc < 0 ? rc : SOSWSOD_OK;
+        }
+    }
     if (grad_dtype == SOSWSOD_DTYPE_F32) {
         if (argmax_dtype == SOSWSOD_ARGMAX_I32)
             return launch_bwd<float, int32_t>(grad_out, ld_grad, argmax, rois, num_rois, row_scale, row_scale_bias, n, c, h, w, pooled_h, pooled_w, spatial_scale, grad_feat, st);
@@ -859,4 +851,24 @@ extern "C" int soswsod_roi_pool_backward(const void* grad_out, int grad_dtype, l
     if (argmax_dtype == SOSWSOD_ARGMAX_I32)
         return launch_bwd<__nv_bfloat16, int32_t>(grad_out, ld_grad, argmax, rois, num_rois, row_scale, row_scale_bias, n, c, h, w, pooled_h, pooled_w, spatial_scale, grad_feat, st);
     return launch_bwd<__nv_bfloat16, uint16_t>(grad_out, ld_grad, argmax, rois, num_rois, row_scale, row_scale_bias, n, c, h, w, pooled_h, pooled_w, spatial_scale, grad_feat, st);
+}
+
+extern "C" size_t soswsod_roi_pool_plan_bytes(int num_rois, int pooled_h, int pooled_w) {
+    if (pooled_h != kPlanP || pooled_w != kPlanP || num_rois <= 0) return 0;
+    return plan_total_bytes(num_rois);
+}
+
+extern "C" int soswsod_roi_pool_plan(const float* rois, int num_rois, int n, int h, int w, int pooled_h, int pooled_w,
+                                     float spatial_scale, const float* row_scale, float row_scale_bias, void* plan,
+                                     size_t plan_bytes, soswsod_stream_t stream) {
+    SOSWSOD_CHECK_ARG(pooled_h == kPlanP && pooled_w == kPlanP, "roi_pool_plan: only 7x7 bins have a plan");
+    SOSWSOD_CHECK_ARG(rois && plan && num_rois > 0, "roi_pool_plan: null pointer / no rois");
+    SOSWSOD_CHECK_ARG(n > 0 && n <= kPlanMaxImages, "roi_pool_plan: 1..%d images per call", kPlanMaxImages);
+    SOSWSOD_CHECK_ARG(h > 0 && w > 0 && h < 65536 && w < 65536, "roi_pool_plan: bad plane size");
+    SOSWSOD_CHECK_ARG((reinterpret_cast<uintptr_t>(plan) & 127) == 0, "roi_pool_plan: plan must be 128-byte aligned");
+    if (plan_bytes < plan_total_bytes(num_rois)) {
+        set_error("roi_pool_plan: plan of %zu bytes, need %zu", plan_bytes, plan_total_bytes(num_rois));
+        return SOSWSOD_ERR_WORKSPACE;
+    }
+    return launch_roi_plan(rois, num_rois, n, h, w, spatial_scale, row_scale, row_scale_bias, plan, (cudaStream_t)stream);
 }

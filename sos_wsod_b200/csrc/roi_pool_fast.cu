@@ -1,0 +1,410 @@
+// ROI max-pool, 7 x 7 bins, the head engine's operand mode (bf16 value * (objectness + 1) and uint16 arg-max):
+// the fast forward / backward kernels behind soswsod_roi_pool_forward / _backward when a plan is supplied.
+//
+//   roi_plan_kernel        per call: groups the rois by image and stores, per roi, its 7 + 7 bin bounds, its scale
+//                          factor and the backward's colour strides (64 bytes) -- bin arithmetic is done ONCE per roi
+//                          instead of once per (roi, channel group) and per direction.
+//   roi_pool_fwd_fast      channel-interleaved planes in shared memory ([cell][CI] fp32, one 128-bit load = one cell
+//                          of 4 channels) plus a table of 1 x 4 row-window first-maxima of the same layout and a byte
+//                          table of their offsets: a bin row of up to 8 cells costs two loads, the arg-max is the
+//                          winning window's cell plus one byte lookup.  Exactly torchvision's result: strict '>' in
+//                          row-major order (first maximum wins), empty bin -> (0, -1), the stored value is the
+//                          cell's own bit pattern.
+//   roi_pool_bwd_fast      see the comment above the kernel.
+#include "roi_plan.cuh"
+#include "tma.cuh"
+
+namespace soswsod {
+
+// ------------------------------------------------------------------------------------------------
+// plan
+// ------------------------------------------------------------------------------------------------
+constexpr int kPlanThreads = 1024;
+
+__global__ void __launch_bounds__(kPlanThreads)
+roi_plan_kernel(const float* __restrict__ rois, int R, int n, int H, int W, float spatial_scale,
+                const float* __restrict__ row_scale, float row_scale_bias, uint8_t* __restrict__ plan) {
+    __shared__ int s_warp[32];
+    __shared__ int s_base[2];
+    const int b = blockIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int* img_start = reinterpret_cast<int*>(plan);
+    int* order = reinterpret_cast<int*>(plan + kPlanHeaderBytes);
+    RoiRecord* rec = reinterpret_cast<RoiRecord*>(plan + plan_records_offset(R));
+
+    // rois of earlier images (start of this image's segment) and of this image
+    int before = 0, mine = 0;
+    for (int r = threadIdx.x; r < R; r += kPlanThreads) {
+        const int rb = (int)rois[(size_t)r * 5];
+        before += (rb >= 0 && rb < b) ? 1 : 0;
+        mine += (rb == b) ? 1 : 0;
+    }
+    before = warp_sum_int(before);
+    mine = warp_sum_int(mine);
+    if (threadIdx.x < 2) s_base[threadIdx.x] = 0;
+    __syncthreads();
+    if (lane == 0) {
+        atomicAdd(&s_base[0], before);   // integer bookkeeping
+        atomicAdd(&s_base[1], mine);
+    }
+    __syncthreads();
+    const int start = s_base[0];
+    if (threadIdx.x == 0) {
+        img_start[b] = start;
+        if (b == n - 1) img_start[n] = start + s_base[1];
+    }
+    // stable compaction of this image's roi indices + the records
+    int base = start;
+    for (int r0 = 0; r0 < R; r0 += kPlanThreads) {
+        const int r = r0 + threadIdx.x;
+        bool flag = false;
+        if (r < R) flag = ((int)rois[(size_t)r * 5] == b);
+        const unsigned bal = __ballot_sync(FULL_MASK, flag);
+        if (lane == 0) s_warp[warp] = __popc(bal);
+        __syncthreads();
+        int wpre = 0, tot = 0;
+        for (int i = 0; i < 32; ++i) {
+            const int c = s_warp[i];
+            wpre += (i < warp) ? c : 0;
+            tot += c;
+        }
+        if (flag) {
+            order[base + wpre + __popc(bal & ((1u << lane) - 1u))] = r;
+            const RoiGeom g = roi_geometry(rois + (size_t)r * 5, spatial_scale, kPlanP, kPlanP);
+            RoiRecord rc;
+#pragma unroll
+            for (int p = 0; p < kPlanP; ++p) {
+                rc.hb[p][0] = (uint16_t)bin_start(p, g.bin_h, g.rs_h, H);
+                rc.hb[p][1] = (uint16_t)bin_end(p, g.bin_h, g.rs_h, H);
+                rc.wb[p][0] = (uint16_t)bin_start(p, g.bin_w, g.rs_w, W);
+                rc.wb[p][1] = (uint16_t)bin_end(p, g.bin_w, g.rs_w, W);
+            }
+            rc.mh = (uint8_t)max(bin_disjoint_stride(g.bin_h, g.rs_h, kPlanP, H), 2);
+            rc.mw = (uint8_t)max(bin_disjoint_stride(g.bin_w, g.rs_w, kPlanP, W), 2);
+            rc.batch = (uint16_t)b;
+            rc.scale = row_scale ? __fadd_rn(row_scale[r], row_scale_bias) : 1.f;
+            const uint4* s4 = reinterpret_cast<const uint4*>(&rc);
+            uint4* d4 = reinterpret_cast<uint4*>(rec + r);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) d4[i] = s4[i];
+        }
+        base += tot;
+        __syncthreads();
+    }
+}
+
+int launch_roi_plan(const float* rois, int R, int n, int h, int w, float scale, const float* row_scale, float bias,
+                    void* plan, cudaStream_t st) {
+    roi_plan_kernel<<<n, kPlanThreads, 0, st>>>(rois, R, n, h, w, scale, row_scale, bias, static_cast<uint8_t*>(plan));
+    SOSWSOD_CHECK_LAUNCH();
+    return SOSWSOD_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// forward
+// ------------------------------------------------------------------------------------------------
+constexpr int kFastThreads = 1024;
+constexpr int kFastWarps = kFastThreads / 32;
+constexpr int kPP = kPlanP * kPlanP;
+
+template <int CI>
+__device__ __forceinline__ void ld_cell(float (&v)[CI], const float* p) {
+    if constexpr (CI == 4) {
+        const float4 t = *reinterpret_cast<const float4*>(p);
+        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    } else if constexpr (CI == 2) {
+        const float2 t = *reinterpret_cast<const float2*>(p);
+        v[0] = t.x; v[1] = t.y;
+    } else {
+        v[0] = *p;
+    }
+}
+template <int CI>
+__device__ __forceinline__ void st_cell(float* p, const float (&v)[CI]) {
+    if constexpr (CI == 4) {
+        *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    } else if constexpr (CI == 2) {
+        *reinterpret_cast<float2*>(p) = make_float2(v[0], v[1]);
+    } else {
+        *p = v[0];
+    }
+}
+
+__device__ __forceinline__ uint32_t pack_out(float val, float scl, int idx) {
+    const __nv_bfloat16 hv = __float2bfloat16_rn(__fmul_rn(val, scl));
+    return ((uint32_t)__bfloat16_as_ushort(hv) << 16) | (uint32_t)(idx < 0 ? 0xFFFF : idx);
+}
+
+// One bin per lane, CI channels at once.  NL loads per bin row: DIRECT reads NL cells of the plane (bins at most 4
+// wide), otherwise NL windows of the 1 x 4 table (bins 4 .. 4*NL wide); `off` are the cell offsets of the loads
+// inside the bin row (clamped into the lane's own bin, so a narrower lane re-reads a cell instead of masking; a
+// re-read never wins the strict '>').  Per channel the lane keeps the running maximum and the cell index of the
+// load that raised it; for a window that is the window's first cell, and the byte table `otab` ([cell][CI]) gives
+// the offset of the first maximum inside the window.  Table entries carry the bit pattern of that first maximum
+// (or -FLT_MAX when no cell of the window beats -FLT_MAX), so value and index equal torchvision's scan exactly.
+template <int CI, int NL, bool DIRECT>
+__device__ __forceinline__ void pool_bin(const float* __restrict__ xs, const float* __restrict__ tab,
+                                         const uint8_t* __restrict__ otab, int W, int hs, int nrows, int nrmax, int ws,
+                                         const int (&off)[NL], float scl, uint32_t* __restrict__ sp) {
+    float m[CI];
+    int pos[CI];
+#pragma unroll
+    for (int c = 0; c < CI; ++c) {
+        m[c] = -FLT_MAX;
+        pos[c] = -1;
+    }
+    int rowcell = hs * W + ws;
+    const float* src = (DIRECT ? xs : tab) + rowcell * CI;
+    const int rstride = W * CI;
+    for (int h = 0; h < nrmax; ++h, src += rstride, rowcell += W) {
+        if (h < nrows) {
+#pragma unroll
+            for (int t = 0; t < NL; ++t) {
+                float v[CI];
+                ld_cell<CI>(v, src + off[t] * CI);
+                const int wc = rowcell + off[t];
+#pragma unroll
+                for (int c = 0; c < CI; ++c)
+                    if (v[c] > m[c]) {
+                        m[c] = v[c];
+                        pos[c] = wc;
+                    }
+            }
+        }
+    }
+    const bool empty = nrows <= 0;   // bw == 0 lanes arrive with nrows = 0
+#pragma unroll
+    for (int c = 0; c < CI; ++c) {
+        float outv = empty ? 0.f : -FLT_MAX;
+        int idx = -1;
+        if (pos[c] >= 0) {
+            outv = m[c];
+            idx = pos[c];
+            if (!DIRECT) idx += otab[pos[c] * CI + c];
+        }
+        sp[c * kPP] = pack_out(outv, scl, idx);
+    }
+}
+
+// Any bin shape (bins clipped at the plane border, bins wider than 16 cells): plain scan, one bin per lane.
+template <int CI>
+__device__ __forceinline__ void pool_bin_generic(const float* __restrict__ xs, int W, int hs, int he, int ws, int we,
+                                                 float scl, uint32_t* __restrict__ sp) {
+    const bool empty = he <= hs || we <= ws;
+#pragma unroll
+    for (int c = 0; c < CI; ++c) {
+        float m = -FLT_MAX;
+        int idx = -1;
+        for (int h = hs; h < he; ++h)
+            for (int w = ws; w < we; ++w) {
+                const float v = xs[(h * W + w) * CI + c];
+                if (v > m) {
+                    m = v;
+                    idx = h * W + w;
+                }
+            }
+        sp[c * kPP] = pack_out(empty ? 0.f : m, scl, idx);
+    }
+}
+
+template <int CI>
+__global__ void __launch_bounds__(kFastThreads, 1)
+roi_pool_fwd_fast_kernel(const float* __restrict__ feat, int C, int H, int W, const int* __restrict__ img_start,
+                         const int* __restrict__ order, const RoiRecord* __restrict__ rec,
+                         uint16_t* __restrict__ argmax_u16, __nv_bfloat16* __restrict__ out_bf16, long long ld_bf16,
+                         int cells_pad, int chunks) {
+    extern __shared__ __align__(16) float smem[];
+    float* xs = smem;                                   // [cells_pad][CI]
+    float* tab = xs + (size_t)cells_pad * CI;           // [cells_pad][CI]  first maximum of cells i .. i+3
+    uint32_t* stage = reinterpret_cast<uint32_t*>(tab + (size_t)cells_pad * CI);   // [warps][CI * 49]
+    uint8_t* otab = reinterpret_cast<uint8_t*>(stage + kFastWarps * CI * kPP);     // [cells_pad][CI]  its offset 0..3
+    const int HW = H * W;
+    const int groups = C / CI;
+    const int b = blockIdx.x / groups;
+    const int c0 = (blockIdx.x % groups) * CI;
+
+    // ---- stage the CI planes channel-interleaved, then the window table ----
+    {
+        const float* src = feat + ((size_t)b * C + c0) * HW;
+        for (int i = threadIdx.x; i < cells_pad; i += kFastThreads) {
+            float v[CI];
+#pragma unroll
+            for (int c = 0; c < CI; ++c) v[c] = i < HW ? __ldg(src + (size_t)c * HW + i) : 0.f;
+            st_cell<CI>(xs + i * CI, v);
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < cells_pad; i += kFastThreads) {
+            float v[CI];
+            uint32_t o = 0;
+#pragma unroll
+            for (int c = 0; c < CI; ++c) v[c] = -FLT_MAX;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                float u[CI];
+                ld_cell<CI>(u, xs + min(i + k, cells_pad - 1) * CI);
+#pragma unroll
+                for (int c = 0; c < CI; ++c)
+                    if (u[c] > v[c]) {
+                        v[c] = u[c];
+                        o = (o & ~(0xFFu << (8 * c))) | ((uint32_t)k << (8 * c));
+                    }
+            }
+            st_cell<CI>(tab + i * CI, v);
+            if constexpr (CI == 4) reinterpret_cast<uint32_t*>(otab)[i] = o;
+            else if constexpr (CI == 2) reinterpret_cast<uint16_t*>(otab)[i] = (uint16_t)o;
+            else otab[i] = (uint8_t)o;
+        }
+        __syncthreads();
+    }
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int sub = lane / kPlanP, pw = lane - sub * kPlanP;
+    const bool active = lane < 4 * kPlanP;
+    uint32_t* sp = stage + warp * (CI * kPP);
+    constexpr int n_out = CI * kPP;
+
+    const int seg_lo = img_start[b], seg_hi = img_start[b + 1];
+    const int per = (seg_hi - seg_lo + chunks - 1) / chunks;
+    const int lo = seg_lo + blockIdx.y * per;
+    const int hi = min(lo + per, seg_hi);
+    for (int i = lo + warp; i < hi; i += kFastWarps) {
+        const int r = __ldg(order + i);
+        const uint32_t* rw = reinterpret_cast<const uint32_t*>(rec + r);
+        uint32_t hb0 = 0, hb1 = 0, wb = 0;
+        if (active) {
+            hb0 = __ldg(rw + sub);
+            if (sub + 4 < kPlanP) hb1 = __ldg(rw + sub + 4);
+            wb = __ldg(rw + kPlanP + pw);
+        }
+        const float scl = __uint_as_float(__ldg(rw + 15));
+        const int ws = (int)(wb & 0xFFFFu), we = (int)(wb >> 16);
+        const int bw = active ? we - ws : 0;
+        const int bwmax = (int)__reduce_max_sync(FULL_MASK, (unsigned)bw);
+        const int bwmin = (int)__reduce_min_sync(FULL_MASK, active ? (unsigned)bw : 0xFFFFu);
+        // 0: direct (bins <= 4 wide), 1: window table, 2: generic
+        const int mode = bwmax <= 4 ? 0 : ((bwmax <= 16 && bwmin >= 4) ? 1 : 2);
+        const int nl = mode == 0 ? max(bwmax, 1) : (bwmax + 3) >> 2;
+#pragma unroll 1
+        for (int s = 0; s < 2; ++s) {
+            const int ph = sub + 4 * s;
+            const bool on = active && ph < kPlanP;
+            const uint32_t hb = s ? hb1 : hb0;
+            const int hs = (int)(hb & 0xFFFFu), he = (int)(hb >> 16);
+            const int nrows = (on && bw > 0) ? he - hs : 0;
+            const int nrmax = (int)__reduce_max_sync(FULL_MASK, (unsigned)nrows);
+            uint32_t* spl = sp + ph * kPlanP + pw;
+            if (mode == 2) {
+                if (on) pool_bin_generic<CI>(xs, W, hs, he, ws, we, scl, spl);
+                continue;
+            }
+            if (!on) {
+                // idle lanes still walk the (uniform) row loop with nrows = 0; they must not write
+                continue;
+            }
+#define SOSWSOD_DIRECT(NLV)                                                                       \
+    case NLV: {                                                                                   \
+        int off[NLV];                                                                             \
+        _Pragma("unroll") for (int t = 0; t < NLV; ++t) off[t] = max(min(t, bw - 1), 0);           \
+        pool_bin<CI, NLV, true>(xs, tab, otab, W, hs, nrows, nrmax, ws, off, scl, spl);             \
+    } break;
+#define SOSWSOD_TABLE(NLV)                                                                        \
+    case NLV: {                                                                                   \
+        int off[NLV];                                                                             \
+        _Pragma("unroll") for (int t = 0; t < NLV; ++t) off[t] = min(4 * t, bw - 4);              \
+        pool_bin<CI, NLV, false>(xs, tab, otab, W, hs, nrows, nrmax, ws, off, scl, spl);            \
+    } break;
+            if (mode == 0) {
+                switch (nl) {
+                    SOSWSOD_DIRECT(1) SOSWSOD_DIRECT(2) SOSWSOD_DIRECT(3) SOSWSOD_DIRECT(4)
+                }
+            } else {
+                switch (nl) {
+                    SOSWSOD_TABLE(2) SOSWSOD_TABLE(3) SOSWSOD_TABLE(4)
+                }
+            }
+#undef SOSWSOD_DIRECT
+#undef SOSWSOD_TABLE
+        }
+        __syncwarp();
+        // ---- coalesced write-out of the roi's CI*49 (value, arg-max) pairs ----
+        uint16_t* adst = argmax_u16 + ((size_t)r * C + c0) * kPP;
+        uint16_t* vdst = reinterpret_cast<uint16_t*>(out_bf16 + (size_t)r * ld_bf16 + (size_t)c0 * kPP);
+        if (CI == 4) {
+            for (int q = lane; q < n_out / 4; q += 32) {
+                const uint4 w4 = *reinterpret_cast<const uint4*>(sp + 4 * q);
+                uint2 a, v;
+                a.x = (w4.x & 0xFFFFu) | (w4.y << 16);
+                a.y = (w4.z & 0xFFFFu) | (w4.w << 16);
+                v.x = (w4.x >> 16) | (w4.y & 0xFFFF0000u);
+                v.y = (w4.z >> 16) | (w4.w & 0xFFFF0000u);
+                reinterpret_cast<uint2*>(adst)[q] = a;
+                reinterpret_cast<uint2*>(vdst)[q] = v;
+            }
+        } else {
+            for (int q = lane; q < n_out / 2; q += 32) {
+                const uint2 w2 = *reinterpret_cast<const uint2*>(sp + 2 * q);
+                reinterpret_cast<uint32_t*>(adst)[q] = (w2.x & 0xFFFFu) | (w2.y << 16);
+                reinterpret_cast<uint32_t*>(vdst)[q] = (w2.x >> 16) | (w2.y & 0xFFFF0000u);
+            }
+        }
+        __syncwarp();
+    }
+}
+
+template <int CI>
+static int launch_fwd_fast_ci(const float* feat, int n, int c, int h, int w, int R, const PlanView& pv, uint16_t* a16,
+                              __nv_bfloat16* obf, long long ld, int cells_pad, size_t smem, cudaStream_t st) {
+    const int groups = n * (c / CI);
+    const int sms = device_num_sms();
+    // rois of an image are split over `chunks` CTAs per channel group: fill whole waves of the SMs (1 CTA/SM) with
+    // the smallest tail, but keep chunks long enough that staging the planes stays a small part of a CTA's work
+    const int per_img = max(1, R / max(n, 1));
+    const int max_chunks = max(1, min(16, per_img / (2 * kFastWarps)));
+    int chunks = 1;
+    double best = 1e30;
+    for (int ch = 1; ch <= max_chunks; ++ch) {
+        const int waves = (groups * ch + sms - 1) / sms;
+        const double cost = (double)waves / ch + 0.004 * ch;
+        if (cost < best - 1e-9) {
+            best = cost;
+            chunks = ch;
+        }
+    }
+    auto kern = roi_pool_fwd_fast_kernel<CI>;
+    SOSWSOD_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<dim3(groups, chunks), kFastThreads, smem, st>>>(feat, c, h, w, pv.img_start, pv.order, pv.rec, a16, obf, ld,
+                                                          cells_pad, chunks);
+    SOSWSOD_CHECK_LAUNCH();
+    return 1;
+}
+
+int launch_fwd_fast(const float* feat, int n, int c, int h, int w, int R, const void* plan, uint16_t* argmax_u16,
+                    __nv_bfloat16* out_bf16, long long ld_bf16, cudaStream_t st) {
+    if (!argmax_u16 || !out_bf16 || n > kPlanMaxImages || (long long)h * w >= 65535) return 0;
+    const int HW = h * w;
+    const int cells_pad = (HW + 4 + 3) / 4 * 4;
+    const size_t max_smem = (size_t)device_max_smem();
+    const PlanView pv = plan_view(plan, R);
+    const bool al8 = (reinterpret_cast<uintptr_t>(argmax_u16) & 7) == 0 && (reinterpret_cast<uintptr_t>(out_bf16) & 7) == 0 &&
+                     ((ld_bf16 * 2) & 7) == 0 && (((long long)c * kPP * 2) & 7) == 0;
+    const bool al4 = (reinterpret_cast<uintptr_t>(argmax_u16) & 3) == 0 && (reinterpret_cast<uintptr_t>(out_bf16) & 3) == 0 &&
+                     ((ld_bf16 * 2) & 3) == 0 && (((long long)c * kPP * 2) & 3) == 0;
+    {
+        const size_t smem = (size_t)cells_pad * 4 * 4 * 2 + (size_t)kFastWarps * 4 * kPP * 4 + (size_t)cells_pad * 4;
+        if (c % 4 == 0 && al8 && smem <= max_smem)
+            return launch_fwd_fast_ci<4>(feat, n, c, h, w, R, pv, argmax_u16, out_bf16, ld_bf16, cells_pad, smem, st);
+    }
+    {
+        const size_t smem = (size_t)cells_pad * 2 * 4 * 2 + (size_t)kFastWarps * 2 * kPP * 4 + (size_t)cells_pad * 2;
+        if (c % 2 == 0 && al4 && smem <= max_smem)
+            return launch_fwd_fast_ci<2>(feat, n, c, h, w, R, pv, argmax_u16, out_bf16, ld_bf16, cells_pad, smem, st);
+    }
+    return 0;
+}
+
+int launch_bwd_fast(const void*, int, long long, const uint16_t*, int, const void*, int, int, int, int, float*,
+                    cudaStream_t) {
+    return 0;
+}
+
+}  // namespace soswsod

@@ -162,12 +162,15 @@ class OICRPlusHeadEngine:
         for f, r in zip(vb.feats, vb.rois):
             m = r.size(0)
             u16 = f.size(2) * f.size(3) < 65535
+            # per-call plan: rois grouped by image + bin bounds / scale / backward colouring per roi (7x7 only)
+            plan = ops.roi_pool_plan(r, tuple(f.shape), (cfg.pooled, cfg.pooled), cfg.spatial_scale,
+                                     row_scale=vb.obj[row:row + m], row_scale_bias=1.0) if u16 else None
             _, am, _ = ops.roi_pool_forward(f, r, (cfg.pooled, cfg.pooled), cfg.spatial_scale,
                                             row_scale=vb.obj[row:row + m], row_scale_bias=1.0, want_f32=False,
-                                            argmax_u16=u16, out_bf16=X[row:row + m])
-            argmaxes.append(am if keep_argmax else None)
+                                            argmax_u16=u16, out_bf16=X[row:row + m], plan=plan)
+            argmaxes.append((am, plan) if keep_argmax else None)
             row += m
-            self.launches_last_step += 1
+            self.launches_last_step += 1 + (plan is not None)
         return X, argmaxes
 
     def _trunk(self, X, train: bool, seeds: Tuple[int, int]):
@@ -244,11 +247,11 @@ class OICRPlusHeadEngine:
             dX = ops.gemm_bf16(dH6, op.w6, b_mn=True, out_dtype=torch.bfloat16)
             self.launches_last_step += 1
             row = 0
-            for f, r, am in zip(vb.feats, vb.rois, argmaxes):
+            for f, r, (am, plan) in zip(vb.feats, vb.rois, argmaxes):
                 m = r.size(0)
                 grad_feats.append(ops.roi_pool_backward(dX[row:row + m], am, r, tuple(f.shape), (cfg.pooled, cfg.pooled),
                                                         row_scale=vb.obj[row:row + m], row_scale_bias=1.0,
-                                                        spatial_scale=cfg.spatial_scale))
+                                                        spatial_scale=cfg.spatial_scale, plan=plan))
                 row += m
                 self.launches_last_step += 1
         grads = {"fc1_w": dW6, "fc1_b": db6, "fc2_w": dW7, "fc2_b": db7}

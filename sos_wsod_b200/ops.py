@@ -44,13 +44,37 @@ def _dt(t: torch.Tensor) -> int:
 # ------------------------------------------------------------------------------------------------
 # (1) ROI max-pool
 # ------------------------------------------------------------------------------------------------
+def roi_pool_plan(rois: torch.Tensor, feat_shape, pooled: Tuple[int, int] = (7, 7), spatial_scale: float = 0.125,
+                  row_scale: Optional[torch.Tensor] = None, row_scale_bias: float = 0.0) -> Optional[torch.Tensor]:
+    """The per-call plan of the fast 7x7 kernels (rois grouped by image + every roi's bin bounds, scale factor and
+    backward colouring), or None when the shape has no plan.  Pass it to roi_pool_forward / roi_pool_backward called
+    with the SAME rois, feature shape, spatial_scale and row_scale."""
+    _need_cuda(rois, row_scale)
+    n, c, h, w = feat_shape
+    m = rois.size(0)
+    lib = _lib.load()
+    nbytes = lib.soswsod_roi_pool_plan_bytes(m, pooled[0], pooled[1])
+    if nbytes == 0 or n > 64 or h >= 65536 or w >= 65536:
+        return None
+    rois = rois.contiguous()
+    if row_scale is not None:
+        row_scale = row_scale.contiguous().float()
+    plan = torch.empty((nbytes + 127) // 128 * 128, dtype=torch.uint8, device=rois.device)
+    check(lib.soswsod_roi_pool_plan(_ptr(rois), m, n, h, w, pooled[0], pooled[1], float(spatial_scale), _ptr(row_scale),
+                                    float(row_scale_bias), _ptr(plan), plan.numel(), _stream()), "roi_pool_plan")
+    _count(1)
+    return plan
+
+
 def roi_pool_forward(feat: torch.Tensor, rois: torch.Tensor, pooled: Tuple[int, int] = (7, 7),
                      spatial_scale: float = 0.125, row_scale: Optional[torch.Tensor] = None,
                      row_scale_bias: float = 0.0, want_f32: bool = True, want_bf16: bool = False,
-                     argmax_u16: bool = False, out_bf16: Optional[torch.Tensor] = None):
+                     argmax_u16: bool = False, out_bf16: Optional[torch.Tensor] = None,
+                     plan: Optional[torch.Tensor] = None):
     """feat fp32 [N,C,H,W], rois fp32 [M,5] -> (out_f32 [M,C,ph,pw] | None, argmax [M,C,ph,pw], out_bf16 [M, C*ph*pw] | None).
-    out_bf16 = pooled * (row_scale + row_scale_bias), the fc6 GEMM operand."""
-    _need_cuda(feat, rois, row_scale)
+    out_bf16 = pooled * (row_scale + row_scale_bias), the fc6 GEMM operand.  `plan` (roi_pool_plan) selects the fast
+    7x7 operand-mode kernel; results are identical without it."""
+    _need_cuda(feat, rois, row_scale, plan)
     assert feat.dtype == torch.float32 and rois.dtype == torch.float32 and rois.dim() == 2 and rois.size(1) == 5
     feat = feat.contiguous()
     rois = rois.contiguous()
@@ -73,7 +97,8 @@ def roi_pool_forward(feat: torch.Tensor, rois: torch.Tensor, pooled: Tuple[int, 
     lib = _lib.load()
     check(lib.soswsod_roi_pool_forward(_ptr(feat), n, c, h, w, _ptr(rois), m, ph, pw, float(spatial_scale),
                                        _ptr(row_scale), float(row_scale_bias), _ptr(out), _ptr(argmax),
-                                       ARGMAX_U16 if argmax_u16 else ARGMAX_I32, _ptr(obf), ld, _stream()),
+                                       ARGMAX_U16 if argmax_u16 else ARGMAX_I32, _ptr(obf), ld, _ptr(plan),
+                                       0 if plan is None else plan.numel(), _stream()),
           "roi_pool_forward")
     _count(1)
     return out, argmax, obf
@@ -81,10 +106,11 @@ def roi_pool_forward(feat: torch.Tensor, rois: torch.Tensor, pooled: Tuple[int, 
 
 def roi_pool_backward(grad_out: torch.Tensor, argmax: torch.Tensor, rois: torch.Tensor, feat_shape,
                       pooled: Tuple[int, int] = (7, 7), row_scale: Optional[torch.Tensor] = None,
-                      row_scale_bias: float = 0.0, spatial_scale: float = 0.125) -> torch.Tensor:
+                      row_scale_bias: float = 0.0, spatial_scale: float = 0.125,
+                      plan: Optional[torch.Tensor] = None) -> torch.Tensor:
     """grad_out [M, C*ph*pw] (or [M,C,ph,pw]) fp32/bf16 -> grad_feat fp32 [N,C,H,W] (overwritten, atomic-free).
-    `argmax` must come from roi_pool_forward on the same rois and spatial_scale."""
-    _need_cuda(grad_out, argmax, rois)
+    `argmax` must come from roi_pool_forward on the same rois and spatial_scale; `plan` as in roi_pool_forward."""
+    _need_cuda(grad_out, argmax, rois, plan)
     n, c, h, w = feat_shape
     ph, pw = pooled
     m = rois.size(0)
@@ -102,7 +128,8 @@ def roi_pool_backward(grad_out: torch.Tensor, argmax: torch.Tensor, rois: torch.
     lib = _lib.load()
     check(lib.soswsod_roi_pool_backward(_ptr(grad_out), _dt(grad_out), grad_out.stride(0), _ptr(argmax.contiguous()), a_dt,
                                         _ptr(rois), m, _ptr(row_scale), float(row_scale_bias), n, c, h, w, ph, pw,
-                                        float(spatial_scale), _ptr(grad_feat), _stream()), "roi_pool_backward")
+                                        float(spatial_scale), _ptr(grad_feat), _ptr(plan),
+                                        0 if plan is None else plan.numel(), _stream()), "roi_pool_backward")
     _count(1)
     return grad_feat
 

@@ -171,6 +171,75 @@ def test_roi_pool_backward_tiny_rois(ops, pooled):
     torch.testing.assert_close(gf.cpu(), feat.grad, rtol=1e-4, atol=1e-4)
 
 
+# ---- the planned 7x7 operand-mode kernels (roi_pool_fast.cu) ----
+def _fast_fwd_check(ops, feat, rois, obj):
+    """Forward with a plan: bf16 operand and uint16 arg-max must equal the oracle's bit for bit."""
+    exp_out, exp_arg = ref.roi_pool(feat, rois)
+    N, C, h, w = feat.shape
+    plan = ops.roi_pool_plan(rois.cuda(), (N, C, h, w), row_scale=None if obj is None else obj.cuda(), row_scale_bias=1.0)
+    assert plan is not None
+    _, arg16, obf = ops.roi_pool_forward(feat.cuda(), rois.cuda(), row_scale=None if obj is None else obj.cuda(),
+                                         row_scale_bias=1.0, want_f32=False, want_bf16=True, argmax_u16=True, plan=plan)
+    a = arg16.cpu().to(torch.int32) & 0xFFFF
+    a[a == 0xFFFF] = -1
+    assert torch.equal(a, exp_arg), "argmax indices must be bit-exact"
+    scale = torch.ones(rois.size(0)) if obj is None else obj + 1
+    exp_bf = (exp_out * scale.view(-1, 1, 1, 1)).flatten(1).to(torch.bfloat16)
+    assert torch.equal(obf.cpu().view(torch.int16), exp_bf.view(torch.int16)), "bf16 operand must be bit-exact (incl. the sign of zero)"
+    return plan, arg16
+
+
+@pytest.mark.parametrize("C,h,w,R", [(512, 60, 80, 300), (64, 72, 96, 257), (8, 37, 53, 300), (6, 96, 152, 200),
+                                     (4, 20, 200, 150), (2, 150, 30, 100)])
+def test_roi_pool_fast_forward_bit_exact(ops, C, h, w, R):
+    """CI=4 and CI=2 interleaves, direct / window-table / generic bin modes (bins up to 200/7 cells wide), clipped,
+    malformed, out-of-image and empty rois."""
+    g = _gen(300 + C + h)
+    feat = torch.relu(torch.randn((1, C, h, w), generator=g))
+    boxes = _rois_with_edge_cases(R, h * 8, w * 8, g)
+    rois = ref.boxes_to_pooler_format([boxes])
+    _fast_fwd_check(ops, feat, rois, torch.rand(rois.size(0), generator=g))
+
+
+def test_roi_pool_fast_forward_ties_negative_and_batch(ops):
+    """All-zero channels (every cell ties: the first cell in row-major order must win), negative features, signed
+    zeros, tiny rois (bins narrower than a cell), three images with shuffled roi order and an image without rois."""
+    g = _gen(311)
+    N, C, h, w = 4, 8, 45, 64
+    feat = torch.randn((N, C, h, w), generator=g)
+    feat[:, 0] = 0.0
+    feat[:, 1] = -0.0
+    feat[:, 2] = torch.relu(feat[:, 2])
+    feat[:, 3] = -torch.relu(feat[:, 3])           # <= 0 with many -0.0
+    feat[:, 4] = torch.round(feat[:, 4] * 2) / 2   # heavy ties
+    bl = []
+    for i in range(N):
+        R = 0 if i == 2 else 150
+        x1 = torch.rand(R, generator=g) * (w * 8 - 60)
+        y1 = torch.rand(R, generator=g) * (h * 8 - 60)
+        bw = torch.rand(R, generator=g) * 56 + 1
+        bh = torch.rand(R, generator=g) * 56 + 1
+        bw[::3] = torch.rand(R, generator=g)[::3] * 400 + 1
+        bh[::4] = torch.rand(R, generator=g)[::4] * 300 + 1
+        bl.append(torch.stack([x1, y1, x1 + bw, y1 + bh], 1).round())
+    rois = ref.boxes_to_pooler_format(bl)
+    rois = rois[torch.randperm(rois.size(0), generator=g)].contiguous()
+    _fast_fwd_check(ops, feat, rois, None)
+
+
+def test_roi_pool_fast_matches_general_kernel_at_bench_shape(ops):
+    """BASELINE shape (2 x [512, 72, 96], 2 x 2000 proposals): planned kernel == general kernel, every element."""
+    g = _gen(312)
+    feat = torch.relu(torch.randn((2, 512, 72, 96), generator=g)).cuda()
+    rois = ref.boxes_to_pooler_format([ref.synth_boxes(2000, 576, 768, g) for _ in range(2)]).cuda()
+    obj = torch.rand(rois.size(0), generator=g).cuda()
+    _, a0, x0 = ops.roi_pool_forward(feat, rois, row_scale=obj, row_scale_bias=1.0, want_f32=False, want_bf16=True, argmax_u16=True)
+    plan = ops.roi_pool_plan(rois, feat.shape, row_scale=obj, row_scale_bias=1.0)
+    _, a1, x1 = ops.roi_pool_forward(feat, rois, row_scale=obj, row_scale_bias=1.0, want_f32=False, want_bf16=True, argmax_u16=True, plan=plan)
+    assert torch.equal(a0, a1)
+    assert torch.equal(x0.view(torch.int16), x1.view(torch.int16))
+
+
 # ------------------------------------------------------------------------------------------------
 # (2) GEMM
 # ------------------------------------------------------------------------------------------------
