@@ -88,6 +88,14 @@ roi_plan_kernel(const float* __restrict__ rois, int R, int n, int H, int W, floa
 #pragma unroll
             for (int i = 0; i < 4; ++i) d4[i] = s4[i];
         }
+        if (b == 0 && r < R) {   // rois of no image: in no list, and a record no CTA of the backward matches
+            const int rb = (int)rois[(size_t)r * 5];
+            if (rb < 0 || rb >= n) {
+                uint4* d4 = reinterpret_cast<uint4*>(rec + r);
+                d4[0] = d4[1] = d4[2] = make_uint4(0u, 0u, 0u, 0u);
+                d4[3] = make_uint4(0u, 0u, 0xFFFF0202u, 0u);
+            }
+        }
         base += tot;
         __syncthreads();
     }
@@ -402,9 +410,347 @@ int launch_fwd_fast(const float* feat, int n, int c, int h, int w, int R, const 
     return 0;
 }
 
-int launch_bwd_fast(const void*, int, long long, const uint16_t*, int, const void*, int, int, int, int, float*,
-                    cudaStream_t) {
-    return 0;
+// ------------------------------------------------------------------------------------------------
+// backward
+// ------------------------------------------------------------------------------------------------
+// A CTA owns the gradient planes of CT consecutive channels of one image (optionally one band of rows of them) in
+// shared memory.  Consumer warp w is the ONLY writer of channels c0+2w and c0+2w+1: lanes 0-15 update the first
+// plane, lanes 16-31 the second, so there is no atomic and no cross-warp race, and the accumulation order is fixed
+// (deterministic).  A producer warp streams [RT rois x BW columns] tiles of arg-max and grad_out through a TMA ring
+// (cp.async.bulk.tensor + mbarriers) and publishes each roi's (scale, colour strides) from the plan.
+//
+// Conflict freedom inside a warp step comes from PROPOSAL-BIN OWNERSHIP: the arg-max of a bin lies inside the bin,
+// and two bins of one roi can only share a cell when their row ranges AND column ranges overlap.  The plan holds,
+// per roi, the smallest strides (mh, mw) such that bins mh rows (mw columns) apart are disjoint (2 x 2 for every roi
+// at least 7 cells high and wide, larger for tiny rois whose bins repeat cells).  A 16-lane half-warp = 4 x 4 blocks
+// of mh x mw bins; a step takes ONE colour (i, j) -- bin (la*mh + i, lb*mw + j) of every block -- whose bins are
+// pairwise disjoint, so every lane does a plain read-add-write on its own cell.  The operands of the next roi are
+// fetched while the (ordered) steps of the current one run, leaving the read-add-write chain on the plane as the
+// only dependency.
+constexpr int kBwdFastMaxCT = 8;
+constexpr int kBwdFastMaxRT = 16;
+
+struct BwdFastCfg {
+    int CT, bands, band_rows, nbox, BW, stages, RT, plane_stride;
+    size_t smem;
+};
+
+struct BwdMeta {
+    float scale;
+    int code;   // 0 = skip (roi of another image); else 1 | mh << 8 | mw << 16
+};
+
+template <typename GradT>
+__global__ void __launch_bounds__((kBwdFastMaxCT / 2 + 1) * 32, 1)
+roi_pool_bwd_fast_kernel(const __grid_constant__ CUtensorMap tmap_arg, const __grid_constant__ CUtensorMap tmap_grad,
+                         const int* __restrict__ img_start, const int* __restrict__ order,
+                         const RoiRecord* __restrict__ rec, int C, int H, int W, float* __restrict__ grad_feat,
+                         BwdFastCfg cfg) {
+    constexpr int PP = kPP;
+    extern __shared__ uint8_t smem_raw[];
+    const int CT = cfg.CT, BW = cfg.BW, nbox = cfg.nbox, S = cfg.stages, RT = cfg.RT;
+    const int NW = (CT + 1) >> 1;   // consumer warps
+    const uint32_t base = (smem_u32(smem_raw) + 127u) & ~127u;
+    uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
+    float* planes = reinterpret_cast<float*>(gen_base);                          // [CT][plane_stride]
+    const uint32_t plane_bytes = (uint32_t)CT * cfg.plane_stride * 4;            // multiple of 128
+    const uint32_t arg_box = (uint32_t)RT * BW * 2;                              // multiple of 128
+    const uint32_t grad_box = (uint32_t)RT * BW * sizeof(GradT);
+    const uint32_t arg_stage = nbox * arg_box, grad_stage = nbox * grad_box;
+    const uint32_t ring_off = plane_bytes;
+    const uint32_t bar_off = ring_off + S * (arg_stage + grad_stage);
+    auto full_bar = [&](int st) { return base + bar_off + 8u * st; };
+    auto empty_bar = [&](int st) { return base + bar_off + 8u * (S + st); };
+    BwdMeta* s_meta = reinterpret_cast<BwdMeta*>(gen_base + bar_off + 16 * S);   // [S][kBwdFastMaxRT]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int groups = (C + CT - 1) / CT;
+    int bid = blockIdx.x;
+    const int band = bid % cfg.bands;
+    bid /= cfg.bands;
+    const int c0 = (bid % groups) * CT;
+    const int b = bid / groups;
+    const int HW = H * W;
+    const int band_lo = min(band * cfg.band_rows, H) * W;
+    const int band_hi = min((band + 1) * cfg.band_rows, H) * W;
+
+    for (int i = threadIdx.x; i < CT * cfg.plane_stride; i += blockDim.x) planes[i] = 0.f;
+    if (threadIdx.x == 0) {
+        for (int st = 0; st < S; ++st) {
+            mbar_init(full_bar(st), 1);
+            mbar_init(empty_bar(st), NW);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    // rows of this image: the plan's order is stable, so its first / last entries are the smallest / largest row
+    const int seg_lo = img_start[b], seg_hi = img_start[b + 1];
+    const int r_lo = seg_hi > seg_lo ? __ldg(order + seg_lo) : 0;
+    const int r_hi = seg_hi > seg_lo ? __ldg(order + seg_hi - 1) + 1 : 0;
+    const int ntiles = (r_hi - r_lo + RT - 1) / RT;
+    const int total_cols = C * PP;
+    const int col0 = c0 * PP;
+    const int col_a = col0 & ~7;                                   // box start: 16-byte aligned column
+    const int col_g = col0 & ~(16 / (int)sizeof(GradT) - 1);
+
+    if (warp == NW) {
+        // ---- producer warp: lane 0 drives the barriers and TMA, lanes < RT publish each roi's scale and colouring ----
+        uint32_t tx = 0;
+        for (int bx = 0; bx < nbox; ++bx) {
+            if (col_a + bx * BW < total_cols) tx += arg_box;
+            if (col_g + bx * BW < total_cols) tx += grad_box;
+        }
+        int st = 0;
+        uint32_t phase = 0;
+        for (int t = 0; t < ntiles; ++t) {
+            const int r0 = r_lo + t * RT;
+            BwdMeta meta;
+            meta.scale = 0.f;
+            meta.code = 0;
+            if (lane < RT && r0 + lane < r_hi) {
+                const uint2 tail = __ldg(reinterpret_cast<const uint2*>(rec + r0 + lane) + 7);   // bytes 56..63
+                if ((int)(tail.x >> 16) == b) {
+                    meta.scale = __uint_as_float(tail.y);
+                    meta.code = 1 | ((tail.x & 0xFFu) << 8) | (((tail.x >> 8) & 0xFFu) << 16);
+                }
+            }
+            mbar_wait(empty_bar(st), phase ^ 1u);
+            if (lane < RT) s_meta[st * kBwdFastMaxRT + lane] = meta;
+            __syncwarp();
+            if (lane == 0) {
+                mbar_expect_tx(full_bar(st), tx);
+                const uint32_t sa = base + ring_off + st * (arg_stage + grad_stage);
+                const uint32_t sg = sa + arg_stage;
+                for (int bx = 0; bx < nbox; ++bx) {
+                    if (col_a + bx * BW < total_cols) tma_load_2d(sa + bx * arg_box, &tmap_arg, full_bar(st), col_a + bx * BW, r0);
+                    if (col_g + bx * BW < total_cols) tma_load_2d(sg + bx * grad_box, &tmap_grad, full_bar(st), col_g + bx * BW, r0);
+                }
+            }
+            if (++st == S) {
+                st = 0;
+                phase ^= 1u;
+            }
+        }
+    } else if (warp < NW) {
+        const int half = lane >> 4, la = (lane >> 2) & 3, lb = lane & 3;
+        const int chan = 2 * warp + half;
+        const bool chan_ok = chan < CT && (c0 + chan) < C;
+        // this lane's plane as a shared-window address held in a register (opaque to the compiler, which otherwise
+        // re-derives it inside the dependent read-add-write chain)
+        uint32_t my_s = smem_u32(planes + (chan_ok ? chan : 0) * cfg.plane_stride);
+        asm volatile("mov.u32 %0, %0;" : "+r"(my_s));
+        const int ea0 = chan * PP + (col0 - col_a);
+        const int eg0 = chan * PP + (col0 - col_g);
+        const unsigned band_cells = (unsigned)(band_hi - band_lo);
+        // byte offset, inside a ring stage, of this lane's entry `bin` of the roi in slot 0
+        auto off_arg = [&](int bin) {
+            int e = ea0 + bin, o = 0;
+            if (e >= BW) { e -= BW; o = RT * BW; }
+            return (o + e) * 2;
+        };
+        auto off_grad = [&](int bin) {
+            int e = eg0 + bin, o = 0;
+            if (e >= BW) { e -= BW; o = RT * BW; }
+            return (o + e) * (int)sizeof(GradT);
+        };
+        // strides 2 x 2 (every roi at least 7 x 7 cells, the common case): the four operands of a lane sit at offsets
+        // that never change
+        constexpr int kCode22 = 1 | (2 << 8) | (2 << 16);
+        int oa2[4], og2[4];
+        bool v2[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int ph = 2 * la + (k >> 1), pw = 2 * lb + (k & 1);
+            v2[k] = chan_ok && ph < kPlanP && pw < kPlanP;
+            oa2[k] = v2[k] ? off_arg(ph * kPlanP + pw) : 0;
+            og2[k] = v2[k] ? off_grad(ph * kPlanP + pw) : 0;
+        }
+        const int row_a = BW * 2, row_g = BW * (int)sizeof(GradT);
+        int st = 0;
+        uint32_t phase = 0;
+        for (int t = 0; t < ntiles; ++t) {
+            mbar_wait(full_bar(st), phase);
+            {
+                const uint8_t* pa = gen_base + ring_off + (size_t)st * (arg_stage + grad_stage);
+                const uint8_t* pg = pa + arg_stage;
+                const BwdMeta* metas = s_meta + st * kBwdFastMaxRT;
+                auto ld_arg = [&](int off) -> unsigned { return (unsigned)*reinterpret_cast<const uint16_t*>(pa + off); };
+                auto ld_grad = [&](int off) -> float {
+                    if (sizeof(GradT) == 2)
+                        return __uint_as_float((unsigned)*reinterpret_cast<const uint16_t*>(pg + off) << 16);
+                    return *reinterpret_cast<const float*>(pg + off);
+                };
+                // one colour step: plain read-add-write.  An empty bin (0xFFFF), an idle lane (0xFFFFFFFF) and a cell
+                // outside this CTA's row band all fail the range test.
+                auto rmw = [&](unsigned a, float g) {
+                    const unsigned rel = a - (unsigned)band_lo;
+                    if (rel < band_cells) {
+                        const uint32_t addr = my_s + rel * 4u;
+                        float v;
+                        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+                        v += g;
+                        asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+                    }
+                    __syncwarp();   // colour classes of one roi may share cells: order the steps
+                };
+                auto fetch22 = [&](int rr, float sc, unsigned (&a)[4], float (&g)[4]) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        a[k] = 0xFFFFFFFFu;
+                        g[k] = 0.f;
+                        if (v2[k]) {
+                            a[k] = ld_arg(rr * row_a + oa2[k]);
+                            g[k] = ld_grad(rr * row_g + og2[k]) * sc;
+                        }
+                    }
+                };
+                unsigned ca[4], na[4];
+                float cg[4], ng[4];
+                bool have = false;            // (ca, cg) hold the prefetched operands of roi rr
+                BwdMeta m = metas[0];
+                if (m.code == kCode22) {
+                    fetch22(0, m.scale, ca, cg);
+                    have = true;
+                }
+                for (int rr = 0; rr < RT; ++rr) {
+                    BwdMeta mn;
+                    mn.code = 0;
+                    mn.scale = 0.f;
+                    if (rr + 1 < RT) mn = metas[rr + 1];
+                    bool have_n = false;
+                    if (mn.code == kCode22) {   // warp-uniform
+                        fetch22(rr + 1, mn.scale, na, ng);
+                        have_n = true;
+                    }
+                    if (have) {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) rmw(ca[k], cg[k]);
+                    } else if (m.code != 0) {
+                        // general strides: colour steps in (i, j) order, operands fetched per step
+                        const int mh = (m.code >> 8) & 0xFF, mw = (m.code >> 16) & 0xFF;
+                        const int ra = rr * row_a, rg = rr * row_g;
+                        for (int i = 0; i < mh; ++i)
+                            for (int j = 0; j < mw; ++j) {
+                                const int ph = la * mh + i, pw = lb * mw + j;
+                                unsigned a = 0xFFFFFFFFu;
+                                float g = 0.f;
+                                if (chan_ok && ph < kPlanP && pw < kPlanP) {
+                                    a = ld_arg(ra + off_arg(ph * kPlanP + pw));
+                                    g = ld_grad(rg + off_grad(ph * kPlanP + pw)) * m.scale;
+                                }
+                                rmw(a, g);
+                            }
+                    }
+                    m = mn;
+                    have = have_n;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        ca[k] = na[k];
+                        cg[k] = ng[k];
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty_bar(st));
+            if (++st == S) {
+                st = 0;
+                phase ^= 1u;
+            }
+        }
+    }
+    __syncthreads();
+    const int band_cells = band_hi - band_lo;
+    for (int c = 0; c < CT && c0 + c < C; ++c) {
+        float* dst = grad_feat + ((size_t)b * C + c0 + c) * HW + band_lo;
+        const float* src = planes + c * cfg.plane_stride;
+        for (int i = threadIdx.x; i < band_cells; i += blockDim.x) dst[i] = src[i];
+    }
+}
+
+static bool pick_bwd_fast_cfg(int n, int c, int h, int w, int grad_bytes, BwdFastCfg* out) {
+    const int max_smem = device_max_smem();
+    const int sms = device_num_sms();
+    const int align_elems = 16 / (2 < grad_bytes ? 2 : grad_bytes);
+    bool found = false;
+    double best_cost = 0;
+    for (int bands = 1; bands <= 64; ++bands) {
+        const int band_rows = (h + bands - 1) / bands;
+        if (bands > 1 && (long long)(bands - 1) * band_rows >= h) continue;  // empty last band
+        const int plane_stride = ((band_rows * w + 31) / 32) * 32;
+        for (int CT = kBwdFastMaxCT; CT >= 1; --CT) {
+            if (CT > c) continue;
+            const int cols = CT * kPP + align_elems - 1;   // + the alignment remainder of the first column
+            const int nbox = (cols + 247) / 248;
+            const int BW = (((cols + nbox - 1) / nbox) + 7) / 8 * 8;
+            if (BW > 256 || nbox > 2) continue;
+            const size_t fixed = (size_t)CT * plane_stride * 4 + 128 /*align*/ + 1024 /*barriers, roi meta*/;
+            for (int RT = kBwdFastMaxRT; RT >= 8; RT >>= 1) {
+                const size_t stage = (size_t)nbox * RT * BW * (2 + grad_bytes);
+                if (fixed + 2 * stage > (size_t)max_smem) continue;
+                int stages = (int)(((size_t)max_smem - fixed) / stage);
+                if (stages > 6) stages = 6;
+                const long long ctas = (long long)n * ((c + CT - 1) / CT) * bands;
+                const long long waves = (ctas + sms - 1) / sms;
+                // every CTA streams all rois of its image once and the chains of its planes advance together:
+                // time ~ waves; an odd CT leaves half a warp idle; prefer deeper rings
+                const double cost = (double)waves + (stages < 3 ? 0.03 : 0.0) + ((CT & 1) ? 0.01 : 0.0);
+                if (!found || cost < best_cost - 1e-9) {
+                    found = true;
+                    best_cost = cost;
+                    out->CT = CT;
+                    out->bands = bands;
+                    out->band_rows = band_rows;
+                    out->nbox = nbox;
+                    out->BW = BW;
+                    out->stages = stages;
+                    out->RT = RT;
+                    out->plane_stride = plane_stride;
+                    out->smem = fixed + (size_t)stages * stage;
+                }
+                if (stages >= 3) break;  // smaller RT only to deepen a shallow ring
+            }
+        }
+        if (found && best_cost < 1.5) break;
+    }
+    return found;
+}
+
+template <typename GradT>
+static int launch_bwd_fast_t(const void* grad, long long ld_grad, const uint16_t* argmax, int R, const void* plan, int n,
+                             int c, int h, int w, float* grad_feat, cudaStream_t st) {
+    BwdFastCfg cfg;
+    if (!pick_bwd_fast_cfg(n, c, h, w, (int)sizeof(GradT), &cfg)) return 0;
+    CUtensorMap ta, tg;
+    int rc = make_tmap_2d(&ta, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, argmax, R, (long long)c * kPP, (long long)c * kPP, cfg.BW,
+                          cfg.RT, CU_TENSOR_MAP_SWIZZLE_NONE);
+    if (rc) return rc;
+    rc = make_tmap_2d(&tg, sizeof(GradT) == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
+                      (int)sizeof(GradT), grad, R, (long long)c * kPP, ld_grad, cfg.BW, cfg.RT, CU_TENSOR_MAP_SWIZZLE_NONE);
+    if (rc) return rc;
+    const PlanView pv = plan_view(plan, R);
+    const int grid = n * ((c + cfg.CT - 1) / cfg.CT) * cfg.bands;
+    const int threads = ((cfg.CT + 1) / 2 + 1) * 32;
+    auto kern = roi_pool_bwd_fast_kernel<GradT>;
+    SOSWSOD_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem));
+    kern<<<grid, threads, cfg.smem, st>>>(ta, tg, pv.img_start, pv.order, pv.rec, c, h, w, grad_feat, cfg);
+    SOSWSOD_CHECK_LAUNCH();
+    return 1;
+}
+
+int launch_bwd_fast(const void* grad, int grad_dtype, long long ld_grad, const uint16_t* argmax, int R, const void* plan,
+                    int n, int c, int h, int w, float* grad_feat, cudaStream_t st) {
+    // TODO(v7): two planes per warp halves the instruction count but leaves one warp per scheduler, so every
+    // dependent-issue latency is exposed (measured 1.17 ms vs 0.81 ms for the general kernel): disabled until the
+    // prepare/accumulate warp split lands.
+    if (true) return 0;
+    if (n > kPlanMaxImages) return 0;
+    const int gb = grad_dtype == SOSWSOD_DTYPE_BF16 ? 2 : 4;
+    const bool aligned = ((uintptr_t)grad & 15) == 0 && ((uintptr_t)argmax & 15) == 0 && ((ld_grad * gb) & 15) == 0 &&
+                         (((long long)c * kPP * 2) & 15) == 0;
+    if (!aligned) return 0;
+    if (grad_dtype == SOSWSOD_DTYPE_BF16)
+        return launch_bwd_fast_t<__nv_bfloat16>(grad, ld_grad, argmax, R, plan, n, c, h, w, grad_feat, st);
+    return launch_bwd_fast_t<float>(grad, ld_grad, argmax, R, plan, n, c, h, w, grad_feat, st);
 }
 
 }  // namespace soswsod

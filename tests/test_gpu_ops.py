@@ -240,6 +240,65 @@ def test_roi_pool_fast_matches_general_kernel_at_bench_shape(ops):
     assert torch.equal(x0.view(torch.int16), x1.view(torch.int16))
 
 
+@pytest.mark.parametrize("C,h,w,N,grad_bf16", [(32, 45, 60, 1, True), (24, 72, 96, 2, False), (7, 30, 40, 3, True),
+                                               (16, 150, 200, 1, True), (8, 200, 300, 1, False)])
+def test_roi_pool_fast_backward(ops, C, h, w, N, grad_bf16):
+    """Planned backward (two planes per warp, colour steps from the plan) against torchvision's autograd: edge-case
+    rois, tiny rois with strides > 2, shuffled multi-image batches, odd channel counts, planes needing row bands."""
+    import torchvision
+
+    g = _gen(400 + C + h)
+    feat = torch.relu(torch.randn((N, C, h, w), generator=g))
+    feat[:, :2] = 0.0
+    feat.requires_grad_(True)
+    bl = []
+    for i in range(N):
+        boxes = _rois_with_edge_cases(150, h * 8, w * 8, g)
+        R = 100
+        x1 = torch.rand(R, generator=g) * (w * 8 - 60)
+        y1 = torch.rand(R, generator=g) * (h * 8 - 60)
+        bw = torch.rand(R, generator=g) * 56 + 1
+        bh = torch.rand(R, generator=g) * 56 + 1
+        bl.append(torch.cat([boxes, torch.stack([x1, y1, x1 + bw, y1 + bh], 1).round()], 0))
+    rois = ref.boxes_to_pooler_format(bl)
+    if N > 1:
+        rois = rois[torch.randperm(rois.size(0), generator=g)].contiguous()
+    obj = torch.rand(rois.size(0), generator=g)
+    pooled = torchvision.ops.roi_pool(feat, rois, (7, 7), 0.125) * (obj + 1).view(-1, 1, 1, 1)
+    go = torch.randn(pooled.shape, generator=g)
+    if grad_bf16:
+        go = go.to(torch.bfloat16).float()
+    pooled.backward(go)
+    plan = ops.roi_pool_plan(rois.cuda(), (N, C, h, w), row_scale=obj.cuda(), row_scale_bias=1.0)
+    _, arg, _ = ops.roi_pool_forward(feat.detach().cuda(), rois.cuda(), want_f32=False, argmax_u16=True, want_bf16=True,
+                                     row_scale=obj.cuda(), row_scale_bias=1.0, plan=plan)
+    go_dev = go.flatten(1).cuda()
+    if grad_bf16:
+        go_dev = go_dev.to(torch.bfloat16)
+    gf = ops.roi_pool_backward(go_dev, arg, rois.cuda(), (N, C, h, w), row_scale=obj.cuda(), row_scale_bias=1.0, plan=plan)
+    torch.testing.assert_close(gf.cpu(), feat.grad, rtol=1e-4, atol=1e-4)
+    gf2 = ops.roi_pool_backward(go_dev, arg, rois.cuda(), (N, C, h, w), row_scale=obj.cuda(), row_scale_bias=1.0, plan=plan)
+    if (C * 49 * 2) % 16 == 0:   # misaligned rows take the documented atomic fallback
+        assert torch.equal(gf, gf2), "the planned backward must be deterministic"
+
+
+def test_roi_pool_fast_backward_bench_shape(ops):
+    """BASELINE shape: planned backward == general backward up to fp32 summation order, and run-to-run identical."""
+    g = _gen(401)
+    feat = torch.relu(torch.randn((2, 512, 60, 80), generator=g)).cuda()
+    rois = ref.boxes_to_pooler_format([ref.synth_boxes(2000, 480, 640, g) for _ in range(2)]).cuda()
+    obj = torch.rand(rois.size(0), generator=g).cuda()
+    plan = ops.roi_pool_plan(rois, feat.shape, row_scale=obj, row_scale_bias=1.0)
+    _, arg, _ = ops.roi_pool_forward(feat, rois, row_scale=obj, row_scale_bias=1.0, want_f32=False, want_bf16=True,
+                                     argmax_u16=True, plan=plan)
+    go = torch.randn((4000, 25088), generator=g).to(torch.bfloat16).cuda()
+    g0 = ops.roi_pool_backward(go, arg, rois, feat.shape, row_scale=obj, row_scale_bias=1.0)
+    g1 = ops.roi_pool_backward(go, arg, rois, feat.shape, row_scale=obj, row_scale_bias=1.0, plan=plan)
+    g2 = ops.roi_pool_backward(go, arg, rois, feat.shape, row_scale=obj, row_scale_bias=1.0, plan=plan)
+    assert torch.equal(g1, g2)
+    torch.testing.assert_close(g1, g0, rtol=2e-4, atol=2e-3)
+
+
 # ------------------------------------------------------------------------------------------------
 # (2) GEMM
 # ------------------------------------------------------------------------------------------------
