@@ -440,16 +440,21 @@ struct BwdMeta {
     int code;   // 0 = skip (roi of another image); else 1 | mh << 8 | mw << 16
 };
 
+constexpr int kBwdKW = 4;        // warps sharing one pair of planes (they take the rois of a tile in turn)
+constexpr int kBwdMaxSteps = 9;  // colour steps prepared in registers at a time (3 x 3 strides; more are chunked)
+
 template <typename GradT>
-__global__ void __launch_bounds__((kBwdFastMaxCT / 2 + 1) * 32, 1)
+__global__ void __launch_bounds__((kBwdFastMaxCT / 2 * kBwdKW + 1) * 32, 1)
 roi_pool_bwd_fast_kernel(const __grid_constant__ CUtensorMap tmap_arg, const __grid_constant__ CUtensorMap tmap_grad,
                          const int* __restrict__ img_start, const int* __restrict__ order,
                          const RoiRecord* __restrict__ rec, int C, int H, int W, float* __restrict__ grad_feat,
                          BwdFastCfg cfg) {
     constexpr int PP = kPP;
+    constexpr int KW = kBwdKW;
     extern __shared__ uint8_t smem_raw[];
     const int CT = cfg.CT, BW = cfg.BW, nbox = cfg.nbox, S = cfg.stages, RT = cfg.RT;
-    const int NW = (CT + 1) >> 1;   // consumer warps
+    const int NP = (CT + 1) >> 1;   // plane pairs
+    const int NCW = NP * KW;        // consumer warps
     const uint32_t base = (smem_u32(smem_raw) + 127u) & ~127u;
     uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
     float* planes = reinterpret_cast<float*>(gen_base);                          // [CT][plane_stride]
@@ -461,7 +466,10 @@ roi_pool_bwd_fast_kernel(const __grid_constant__ CUtensorMap tmap_arg, const __g
     const uint32_t bar_off = ring_off + S * (arg_stage + grad_stage);
     auto full_bar = [&](int st) { return base + bar_off + 8u * st; };
     auto empty_bar = [&](int st) { return base + bar_off + 8u * (S + st); };
-    BwdMeta* s_meta = reinterpret_cast<BwdMeta*>(gen_base + bar_off + 16 * S);   // [S][kBwdFastMaxRT]
+    auto turn_bar = [&](int cw) { return base + bar_off + 16u * S + 8u * cw; };   // [NCW]
+    const uint32_t meta_off = bar_off + 16u * S + 8u * (kBwdFastMaxCT / 2 * KW);
+    BwdMeta* s_meta = reinterpret_cast<BwdMeta*>(gen_base + meta_off);           // [S][kBwdFastMaxRT]
+    float* s_dummy = reinterpret_cast<float*>(s_meta + S * kBwdFastMaxRT);        // [32] idle-lane targets
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int groups = (C + CT - 1) / CT;
@@ -478,8 +486,9 @@ roi_pool_bwd_fast_kernel(const __grid_constant__ CUtensorMap tmap_arg, const __g
     if (threadIdx.x == 0) {
         for (int st = 0; st < S; ++st) {
             mbar_init(full_bar(st), 1);
-            mbar_init(empty_bar(st), NW);
+            mbar_init(empty_bar(st), NCW);
         }
+        for (int cw = 0; cw < NCW; ++cw) mbar_init(turn_bar(cw), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -493,7 +502,7 @@ roi_pool_bwd_fast_kernel(const __grid_constant__ CUtensorMap tmap_arg, const __g
     const int col_a = col0 & ~7;                                   // box start: 16-byte aligned column
     const int col_g = col0 & ~(16 / (int)sizeof(GradT) - 1);
 
-    if (warp == NW) {
+    if (warp == NCW) {
         // ---- producer warp: lane 0 drives the barriers and TMA, lanes < RT publish each roi's scale and colouring ----
         uint32_t tx = 0;
         for (int bx = 0; bx < nbox; ++bx) {
@@ -531,124 +540,137 @@ roi_pool_bwd_fast_kernel(const __grid_constant__ CUtensorMap tmap_arg, const __g
                 phase ^= 1u;
             }
         }
-    } else if (warp < NW) {
+    } else if (warp < NCW) {
+        // ---- consumer warps.  KW warps serve one pair of planes; the rois (slots) of the stream are dealt to them
+        // round-robin.  A warp PREPARES its roi -- operands of every colour step fetched from the ring and turned into
+        // (shared address, scaled gradient) pairs in registers -- while its predecessors are still accumulating, then
+        // waits for the turn token, runs the ordered read-add-write steps and passes the token on.
+        const int pair = warp / KW, q = warp - pair * KW;
         const int half = lane >> 4, la = (lane >> 2) & 3, lb = lane & 3;
-        const int chan = 2 * warp + half;
+        const int chan = 2 * pair + half;
         const bool chan_ok = chan < CT && (c0 + chan) < C;
-        // this lane's plane as a shared-window address held in a register (opaque to the compiler, which otherwise
-        // re-derives it inside the dependent read-add-write chain)
         uint32_t my_s = smem_u32(planes + (chan_ok ? chan : 0) * cfg.plane_stride);
-        asm volatile("mov.u32 %0, %0;" : "+r"(my_s));
+        uint32_t dummy_s = smem_u32(s_dummy) + 4u * lane;
+        asm volatile("mov.u32 %0, %0;" : "+r"(my_s));       // keep both in registers
+        asm volatile("mov.u32 %0, %0;" : "+r"(dummy_s));
         const int ea0 = chan * PP + (col0 - col_a);
         const int eg0 = chan * PP + (col0 - col_g);
         const unsigned band_cells = (unsigned)(band_hi - band_lo);
-        // byte offset, inside a ring stage, of this lane's entry `bin` of the roi in slot 0
-        auto off_arg = [&](int bin) {
-            int e = ea0 + bin, o = 0;
-            if (e >= BW) { e -= BW; o = RT * BW; }
-            return (o + e) * 2;
-        };
-        auto off_grad = [&](int bin) {
-            int e = eg0 + bin, o = 0;
-            if (e >= BW) { e -= BW; o = RT * BW; }
-            return (o + e) * (int)sizeof(GradT);
-        };
-        // strides 2 x 2 (every roi at least 7 x 7 cells, the common case): the four operands of a lane sit at offsets
-        // that never change
+        const int wrap = (RT - 1) * BW;          // elements skipped when an entry falls into the second box
+        const uint32_t ring_s = base + ring_off;
+        const uint32_t stage_bytes = arg_stage + grad_stage;
+        const uint32_t my_turn = turn_bar(warp), prev_turn = turn_bar(pair * KW + (q + KW - 1) % KW);
+        // strides 2 x 2 (every roi at least 7 x 7 cells): the lane's four bins sit at constant offsets
         constexpr int kCode22 = 1 | (2 << 8) | (2 << 16);
-        int oa2[4], og2[4];
-        bool v2[4];
+        int e22a[4], e22g[4];
+        bool v22[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const int ph = 2 * la + (k >> 1), pw = 2 * lb + (k & 1);
-            v2[k] = chan_ok && ph < kPlanP && pw < kPlanP;
-            oa2[k] = v2[k] ? off_arg(ph * kPlanP + pw) : 0;
-            og2[k] = v2[k] ? off_grad(ph * kPlanP + pw) : 0;
+            v22[k] = chan_ok && ph < kPlanP && pw < kPlanP;
+            int e = ea0 + ph * kPlanP + pw;
+            e22a[k] = e + (e >= BW ? wrap : 0);
+            e = eg0 + ph * kPlanP + pw;
+            e22g[k] = e + (e >= BW ? wrap : 0);
         }
-        const int row_a = BW * 2, row_g = BW * (int)sizeof(GradT);
+
         int st = 0;
         uint32_t phase = 0;
+        int slot = 0;          // global slot counter of the stream
+        int mine = 0;          // slots this warp has handled so far
         for (int t = 0; t < ntiles; ++t) {
             mbar_wait(full_bar(st), phase);
-            {
-                const uint8_t* pa = gen_base + ring_off + (size_t)st * (arg_stage + grad_stage);
-                const uint8_t* pg = pa + arg_stage;
-                const BwdMeta* metas = s_meta + st * kBwdFastMaxRT;
-                auto ld_arg = [&](int off) -> unsigned { return (unsigned)*reinterpret_cast<const uint16_t*>(pa + off); };
-                auto ld_grad = [&](int off) -> float {
-                    if (sizeof(GradT) == 2)
-                        return __uint_as_float((unsigned)*reinterpret_cast<const uint16_t*>(pg + off) << 16);
-                    return *reinterpret_cast<const float*>(pg + off);
-                };
-                // one colour step: plain read-add-write.  An empty bin (0xFFFF), an idle lane (0xFFFFFFFF) and a cell
-                // outside this CTA's row band all fail the range test.
-                auto rmw = [&](unsigned a, float g) {
-                    const unsigned rel = a - (unsigned)band_lo;
-                    if (rel < band_cells) {
-                        const uint32_t addr = my_s + rel * 4u;
-                        float v;
-                        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
-                        v += g;
-                        asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+            const uint32_t sa = ring_s + st * stage_bytes;      // arg-max boxes of this stage
+            const uint32_t sg = sa + arg_stage;                 // grad boxes
+            const BwdMeta* metas = s_meta + st * kBwdFastMaxRT;
+            for (int rr = 0; rr < RT; ++rr, ++slot) {
+                if (slot % KW != q) continue;
+                const BwdMeta m = metas[rr];
+                const int mh = (m.code >> 8) & 0xFF, mw = (m.code >> 16) & 0xFF;
+                const int nsteps = mh * mw;                     // 0 for a roi of another image
+                const int rowe = rr * BW;
+                uint32_t addr[kBwdMaxSteps];
+                float val[kBwdMaxSteps];
+                auto operand = [&](int ea, int eg, uint32_t& ad, float& vl) {
+                    unsigned a, graw;
+                    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(a) : "r"(sa + 2u * (unsigned)(ea + rowe)));
+                    if (sizeof(GradT) == 2) {
+                        asm volatile("ld.shared.u16 %0, [%1];" : "=r"(graw) : "r"(sg + 2u * (unsigned)(eg + rowe)));
+                        graw <<= 16;
+                    } else {
+                        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(graw) : "r"(sg + 4u * (unsigned)(eg + rowe)));
                     }
-                    __syncwarp();   // colour classes of one roi may share cells: order the steps
+                    const unsigned rel = a - (unsigned)band_lo;   // empty bin (0xFFFF) and other bands fail the test
+                    const bool ok = rel < band_cells;
+                    ad = ok ? my_s + 4u * rel : dummy_s;
+                    vl = ok ? __uint_as_float(graw) * m.scale : 0.f;
                 };
-                auto fetch22 = [&](int rr, float sc, unsigned (&a)[4], float (&g)[4]) {
+                bool token = false;
+                auto take_turn = [&]() {
+                    if (!token) {
+                        if (!(q == 0 && mine == 0)) mbar_spin(prev_turn, (uint32_t)((q == 0 ? mine - 1 : mine) & 1));
+                        token = true;
+                    }
+                };
+                if (m.code == kCode22) {
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
-                        a[k] = 0xFFFFFFFFu;
-                        g[k] = 0.f;
-                        if (v2[k]) {
-                            a[k] = ld_arg(rr * row_a + oa2[k]);
-                            g[k] = ld_grad(rr * row_g + og2[k]) * sc;
+                        addr[k] = dummy_s;
+                        val[k] = 0.f;
+                        if (v22[k]) operand(e22a[k], e22g[k], addr[k], val[k]);
+                    }
+                    take_turn();
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        float v;
+                        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr[k]) : "memory");
+                        v += val[k];
+                        asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr[k]), "f"(v) : "memory");
+                        __syncwarp();   // colour classes of one roi may share cells: order the steps
+                    }
+                } else if (nsteps > 0) {
+                    const int bin0 = la * mh * kPlanP + lb * mw;
+                    const int ih = chan_ok ? min(mh, kPlanP - la * mh) : 0;   // <= 0: block outside the grid
+                    const int jw = min(mw, kPlanP - lb * mw);
+                    int i = 0, j = 0;
+                    for (int s0 = 0; s0 < nsteps; s0 += kBwdMaxSteps) {
+                        const int n = min(kBwdMaxSteps, nsteps - s0);
+#pragma unroll
+                        for (int k = 0; k < kBwdMaxSteps; ++k) {
+                            addr[k] = dummy_s;
+                            val[k] = 0.f;
+                            if (k < n) {
+                                if (i < ih && j < jw) {
+                                    const int bin = bin0 + i * kPlanP + j;
+                                    int ea = ea0 + bin, eg = eg0 + bin;
+                                    ea += (ea >= BW ? wrap : 0);
+                                    eg += (eg >= BW ? wrap : 0);
+                                    operand(ea, eg, addr[k], val[k]);
+                                }
+                                if (++j == mw) {
+                                    j = 0;
+                                    ++i;
+                                }
+                            }
+                        }
+                        take_turn();
+#pragma unroll
+                        for (int k = 0; k < kBwdMaxSteps; ++k) {
+                            if (k < n) {
+                                float v;
+                                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr[k]) : "memory");
+                                v += val[k];
+                                asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr[k]), "f"(v) : "memory");
+                                __syncwarp();
+                            }
                         }
                     }
-                };
-                unsigned ca[4], na[4];
-                float cg[4], ng[4];
-                bool have = false;            // (ca, cg) hold the prefetched operands of roi rr
-                BwdMeta m = metas[0];
-                if (m.code == kCode22) {
-                    fetch22(0, m.scale, ca, cg);
-                    have = true;
+                } else {
+                    take_turn();
                 }
-                for (int rr = 0; rr < RT; ++rr) {
-                    BwdMeta mn;
-                    mn.code = 0;
-                    mn.scale = 0.f;
-                    if (rr + 1 < RT) mn = metas[rr + 1];
-                    bool have_n = false;
-                    if (mn.code == kCode22) {   // warp-uniform
-                        fetch22(rr + 1, mn.scale, na, ng);
-                        have_n = true;
-                    }
-                    if (have) {
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) rmw(ca[k], cg[k]);
-                    } else if (m.code != 0) {
-                        // general strides: colour steps in (i, j) order, operands fetched per step
-                        const int mh = (m.code >> 8) & 0xFF, mw = (m.code >> 16) & 0xFF;
-                        const int ra = rr * row_a, rg = rr * row_g;
-                        for (int i = 0; i < mh; ++i)
-                            for (int j = 0; j < mw; ++j) {
-                                const int ph = la * mh + i, pw = lb * mw + j;
-                                unsigned a = 0xFFFFFFFFu;
-                                float g = 0.f;
-                                if (chan_ok && ph < kPlanP && pw < kPlanP) {
-                                    a = ld_arg(ra + off_arg(ph * kPlanP + pw));
-                                    g = ld_grad(rg + off_grad(ph * kPlanP + pw)) * m.scale;
-                                }
-                                rmw(a, g);
-                            }
-                    }
-                    m = mn;
-                    have = have_n;
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        ca[k] = na[k];
-                        cg[k] = ng[k];
-                    }
-                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(my_turn);   // release: the next warp sees this roi's updates
+                ++mine;
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(empty_bar(st));
@@ -683,8 +705,8 @@ static bool pick_bwd_fast_cfg(int n, int c, int h, int w, int grad_bytes, BwdFas
             const int nbox = (cols + 247) / 248;
             const int BW = (((cols + nbox - 1) / nbox) + 7) / 8 * 8;
             if (BW > 256 || nbox > 2) continue;
-            const size_t fixed = (size_t)CT * plane_stride * 4 + 128 /*align*/ + 1024 /*barriers, roi meta*/;
-            for (int RT = kBwdFastMaxRT; RT >= 8; RT >>= 1) {
+            const size_t fixed = (size_t)CT * plane_stride * 4 + 128 /*align*/ + 1536 /*barriers, roi meta, dummies*/;
+            for (int RT = kBwdFastMaxRT; RT >= 4; RT >>= 1) {
                 const size_t stage = (size_t)nbox * RT * BW * (2 + grad_bytes);
                 if (fixed + 2 * stage > (size_t)max_smem) continue;
                 int stages = (int)(((size_t)max_smem - fixed) / stage);
@@ -729,7 +751,7 @@ static int launch_bwd_fast_t(const void* grad, long long ld_grad, const uint16_t
     if (rc) return rc;
     const PlanView pv = plan_view(plan, R);
     const int grid = n * ((c + cfg.CT - 1) / cfg.CT) * cfg.bands;
-    const int threads = ((cfg.CT + 1) / 2 + 1) * 32;
+    const int threads = ((cfg.CT + 1) / 2 * kBwdKW + 1) * 32;
     auto kern = roi_pool_bwd_fast_kernel<GradT>;
     SOSWSOD_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem));
     kern<<<grid, threads, cfg.smem, st>>>(ta, tg, pv.img_start, pv.order, pv.rec, c, h, w, grad_feat, cfg);
@@ -739,10 +761,6 @@ static int launch_bwd_fast_t(const void* grad, long long ld_grad, const uint16_t
 
 int launch_bwd_fast(const void* grad, int grad_dtype, long long ld_grad, const uint16_t* argmax, int R, const void* plan,
                     int n, int c, int h, int w, float* grad_feat, cudaStream_t st) {
-    // TODO(v7): two planes per warp halves the instruction count but leaves one warp per scheduler, so every
-    // dependent-issue latency is exposed (measured 1.17 ms vs 0.81 ms for the general kernel): disabled until the
-    // prepare/accumulate warp split lands.
-    if (true) return 0;
     if (n > kPlanMaxImages) return 0;
     const int gb = grad_dtype == SOSWSOD_DTYPE_BF16 ? 2 : 4;
     const bool aligned = ((uintptr_t)grad & 15) == 0 && ((uintptr_t)argmax & 15) == 0 && ((ld_grad * gb) & 15) == 0 &&
