@@ -125,7 +125,7 @@ int soswsod_colsum(const void* in, int in_dtype, long long ld_in, int rows, int 
 
 /* ---------------------------------------------------------------------------------------------
  * (3) Fused WSDDN two-stream head: scores, image scores, BCE and the gradient w.r.t. both logit
- *     blocks in one launch (one CTA per view).  Replaces WSDDNOutputLayers.forward softmax product
+ *     blocks in one launch (one 8-CTA cluster per view, reductions through distributed shared memory).  Replaces WSDDNOutputLayers.forward softmax product
  *     (W/modeling/roi_heads/fast_rcnn_wsddn.py:566-567), WSDDNOutputs.predict_probs_img (:360-375) and
  *     binary_cross_entropy_loss (:340-358) with MEAN_LOSS.
  *

@@ -150,6 +150,7 @@ class OICRPlusHeadEngine:
         self.op = operands
         self.launches_last_step = 0
         self.grad_hook = None
+        self.deferred_scale_check = None
         self.last_output: Optional[TrainOutput] = None
 
     # -------------------------------------------------------------------------------------------

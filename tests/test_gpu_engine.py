@@ -195,6 +195,23 @@ def test_plugin_surface_train_and_eval(cuda_lib):
             prm.add_(prm.grad, alpha=-1e-3)
     _, losses2 = heads(None, [{"plain5": f1}, {"plain5": f2}], [props(v) for v in views], [targets, None, None, None])
     assert abs(losses2["loss_cls"].item() - losses["loss_cls"].item()) > 0
+    # deferred upstream-gradient check: same gradients without a host stall; a scaled objective is reported late
+    g_sync = heads.box_head.fc2.weight.grad.clone()
+    heads.loss_scale_check = "deferred"
+    for prm in heads.parameters():
+        prm.grad = None
+    with torch.no_grad():
+        for prm in heads.parameters():
+            prm.add_(g_sync.new_zeros(()))   # no-op touch: keep the operand versions as they are
+    _, l3 = heads(None, [{"plain5": f1}, {"plain5": f2}], [props(v) for v in views], [targets, None, None, None])
+    sum(l3.values()).backward()
+    heads.check_deferred(wait=True)
+    assert heads.box_head.fc2.weight.grad is not None
+    _, l4 = heads(None, [{"plain5": f1}, {"plain5": f2}], [props(v) for v in views], [targets, None, None, None])
+    (2.0 * sum(l4.values())).backward()
+    with pytest.raises(NotImplementedError):
+        heads.check_deferred(wait=True)
+    heads.loss_scale_check = "sync"
     # eval
     heads.eval()
     inst, empty, all_scores, all_boxes = heads(None, {"plain5": f1[:1].detach()}, props(views[0]), None)
