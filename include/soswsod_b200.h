@@ -252,6 +252,19 @@ int soswsod_detect(const float* probs, const float* pred_boxes, int R, int C, fl
 int soswsod_sgd_step(float* param, const float* grad, float* momentum_buf, long long n, float lr, float momentum,
                      float weight_decay, float grad_scale, void* param_bf16, soswsod_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * (6) PGF, the consumer of the detection-results json.  Replaces the per-image
+ *     Python loops of tools/pgf.py:221-270 (`pgf`) with `contain_cal` (:210-219), in the same double
+ *     precision: detections of image i are rows [img_offsets[i], img_offsets[i+1]) in list order;
+ *     keep[r] = 1 when row r survives both the keep-threshold rule (first detection of a category
+ *     always kept, later ones need score >= t_keep) and the same-category containment rule
+ *     (area(r ∩ j) / (area(r) + 1e-6) >= t_con drops r; categories in the 128-bit diff mask are exempt
+ *     unless use_diff).  boxes are XYWH doubles [n,4], 32-byte aligned.
+ * ------------------------------------------------------------------------------------------- */
+int soswsod_pgf(const double* boxes_xywh, const double* scores, const int* categories, const int* img_offsets,
+                int num_images, double t_con, double t_keep, int use_diff, unsigned long long diff_mask_lo,
+                unsigned long long diff_mask_hi, unsigned char* keep, soswsod_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -6,7 +6,7 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import c_char_p, c_float, c_int, c_int32, c_int64, c_longlong, c_size_t, c_ulonglong, c_void_p
+from ctypes import c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_longlong, c_size_t, c_ulonglong, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libsoswsod_b200.so")
@@ -50,6 +50,7 @@ SIGNATURES = {
     "soswsod_detect_workspace_bytes": (c_size_t, [c_int, c_int]),
     "soswsod_detect": (c_int, [_P, _P, c_int, c_int, c_float, c_float, c_float, c_float, c_int, _P, _P, _P, _P, _P, _P,
                                 c_size_t, _P]),
+    "soswsod_pgf": (c_int, [_P, _P, _P, _P, c_int, c_double, c_double, c_int, c_ulonglong, c_ulonglong, _P, _P]),
     "soswsod_sgd_step": (c_int, [_P, _P, _P, c_longlong, c_float, c_float, c_float, c_float, _P, _P]),
 }
 

@@ -393,3 +393,29 @@ def detect(probs: torch.Tensor, pred_boxes: torch.Tensor, image_size: Tuple[floa
                              _ptr(dc), _ptr(dr), _ptr(nd), _ptr(workspace), workspace.numel(), _stream()), "detect")
     _count(5)
     return db, ds, dc, dr, nd
+
+
+# ------------------------------------------------------------------------------------------------
+# (6) PGF (tools/pgf.py) on the device
+# ------------------------------------------------------------------------------------------------
+def pgf_filter(boxes_xywh: torch.Tensor, scores: torch.Tensor, cats: torch.Tensor, img_offsets: torch.Tensor,
+               t_con: float, t_keep: float, use_diff: bool, diff_classes) -> torch.Tensor:
+    """boxes float64 [n,4] XYWH, scores float64 [n], cats int32 [n], img_offsets int32 [I+1] -> keep bool [n]."""
+    _need_cuda(boxes_xywh, scores, cats, img_offsets)
+    assert boxes_xywh.dtype == torch.float64 and scores.dtype == torch.float64
+    assert cats.dtype == torch.int32 and img_offsets.dtype == torch.int32
+    boxes_xywh, scores, cats, img_offsets = (t.contiguous() for t in (boxes_xywh, scores, cats, img_offsets))
+    n = scores.numel()
+    keep = torch.empty((n,), dtype=torch.uint8, device=scores.device)
+    lo = hi = 0
+    for c in diff_classes:
+        if not 0 <= int(c) < 128:
+            raise RuntimeError("pgf_filter: diff classes must lie in [0, 128)")
+        if c < 64:
+            lo |= 1 << int(c)
+        else:
+            hi |= 1 << (int(c) - 64)
+    check(_lib.load().soswsod_pgf(_ptr(boxes_xywh), _ptr(scores), _ptr(cats), _ptr(img_offsets), img_offsets.numel() - 1,
+                                  float(t_con), float(t_keep), int(use_diff), lo, hi, _ptr(keep), _stream()), "pgf")
+    _count(1)
+    return keep.bool()
