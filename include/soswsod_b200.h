@@ -119,9 +119,12 @@ int soswsod_cast_f32_bf16(const float* in, long long ld_in, int rows, int cols, 
 /* out_t[c, r] = in[r, c] for bf16 [rows, ld_in]. */
 int soswsod_transpose_bf16(const void* in, long long ld_in, int rows, int cols, void* out_t,
                            long long ld_out_t, soswsod_stream_t stream);
-/* out[c] = sum_r in[r, c] (bias gradients), fixed summation order; in bf16 or fp32 per in_dtype. */
+/* out[c] = sum_r in[r, c] (bias gradients), fixed summation order; in bf16 or fp32 per in_dtype.
+ * With a workspace of soswsod_colsum_workspace_bytes() (16-byte aligned; NULL allowed) the matrix is
+ * streamed once with 16-byte loads into per-chunk partial sums that a second launch adds in chunk order. */
+size_t soswsod_colsum_workspace_bytes(int rows, int cols, int in_dtype);
 int soswsod_colsum(const void* in, int in_dtype, long long ld_in, int rows, int cols, float* out,
-                   soswsod_stream_t stream);
+                   void* workspace, size_t workspace_bytes, soswsod_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * (3) Fused WSDDN two-stream head: scores, image scores, BCE and the gradient w.r.t. both logit

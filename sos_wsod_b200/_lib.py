@@ -33,7 +33,8 @@ SIGNATURES = {
     "soswsod_dropout_mask": (c_int, [_P, c_int, c_int, c_float, c_ulonglong, _P]),
     "soswsod_cast_f32_bf16": (c_int, [_P, _LL, c_int, c_int, _P, _P, _LL, _P, _LL, _P]),
     "soswsod_transpose_bf16": (c_int, [_P, _LL, c_int, c_int, _P, _LL, _P]),
-    "soswsod_colsum": (c_int, [_P, c_int, _LL, c_int, c_int, _P, _P]),
+    "soswsod_colsum_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "soswsod_colsum": (c_int, [_P, c_int, _LL, c_int, c_int, _P, _P, c_size_t, _P]),
     "soswsod_wsddn_forward": (c_int, [_P, _LL, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P, _LL, _P]),
     "soswsod_oicr_avg_scores": (c_int, [_P, _P, _LL, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P]),
     "soswsod_oicr_mine_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),

@@ -88,6 +88,58 @@ colsum_kernel(const T* __restrict__ in, long long ld_in, int rows, int cols, flo
     }
 }
 
+// Two-pass column sum for wide matrices: pass 1 streams the matrix once with 16-byte loads (a thread owns VEC
+// adjacent columns of one row chunk) and writes per-chunk partial sums to the workspace [chunks, cols]; pass 2 adds
+// the chunks of a column in chunk order.  Deterministic, no atomics.
+template <typename T, int VEC>
+__global__ void __launch_bounds__(128)
+colsum_partial_kernel(const T* __restrict__ in, long long ld_in, int rows, int cols, int rows_per_chunk,
+                      float* __restrict__ part) {
+    const int c = (blockIdx.x * 128 + threadIdx.x) * VEC;
+    if (c >= cols) return;
+    const int r0 = blockIdx.y * rows_per_chunk, r1 = min(rows, r0 + rows_per_chunk);
+    float acc[VEC];
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) acc[k] = 0.f;
+    const T* p = in + (size_t)r0 * ld_in + c;
+#pragma unroll 4
+    for (int r = r0; r < r1; ++r, p += ld_in) {
+        const uint4 v = *reinterpret_cast<const uint4*>(p);
+        if (sizeof(T) == 2) {
+            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                acc[2 * k] += __uint_as_float(w[k] << 16);
+                acc[2 * k + 1] += __uint_as_float(w[k] & 0xFFFF0000u);
+            }
+        } else {
+            acc[0] += __uint_as_float(v.x);
+            acc[1] += __uint_as_float(v.y);
+            acc[2] += __uint_as_float(v.z);
+            acc[3] += __uint_as_float(v.w);
+        }
+    }
+    float* dst = part + (size_t)blockIdx.y * cols + c;
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) dst[k] = acc[k];
+}
+
+__global__ void __launch_bounds__(256)
+colsum_final_kernel(const float* __restrict__ part, int chunks, int cols, float* __restrict__ out) {
+    const int c = blockIdx.x * 256 + threadIdx.x;
+    if (c >= cols) return;
+    float s = 0.f;
+    for (int k = 0; k < chunks; ++k) s += part[(size_t)k * cols + c];
+    out[c] = s;
+}
+
+static int colsum_chunks(int rows, int cols, int vec) {
+    const int col_blocks = (cols / vec + 127) / 128;
+    int chunks = (2 * 148 + col_blocks - 1) / col_blocks;
+    if (chunks > (rows + 15) / 16) chunks = (rows + 15) / 16;   // at least 16 rows per chunk
+    return chunks < 1 ? 1 : chunks;
+}
+
 // SGD with momentum and weight decay (torch.optim.SGD semantics, as built by uwsod/detectron2/solver/build.py:
 // g = grad*grad_scale + wd*p ; buf = momentum*buf + g ; p -= lr*buf), fused with the refresh of the bf16 GEMM
 // operand copy of the parameter.
@@ -148,11 +200,37 @@ extern "C" int soswsod_transpose_bf16(const void* in, long long ld_in, int rows,
     return SOSWSOD_OK;
 }
 
+extern "C" size_t soswsod_colsum_workspace_bytes(int rows, int cols, int in_dtype) {
+    const int vec = in_dtype == SOSWSOD_DTYPE_BF16 ? 8 : 4;
+    if (rows <= 0 || cols <= 0 || cols % vec) return 0;
+    return (size_t)colsum_chunks(rows, cols, vec) * cols * 4;
+}
+
 extern "C" int soswsod_colsum(const void* in, int in_dtype, long long ld_in, int rows, int cols, float* out,
-                              soswsod_stream_t stream) {
+                              void* workspace, size_t workspace_bytes, soswsod_stream_t stream) {
     SOSWSOD_CHECK_ARG(in && out, "colsum: null pointer");
     SOSWSOD_CHECK_ARG(rows > 0 && cols > 0 && ld_in >= cols, "colsum: bad shape");
     SOSWSOD_CHECK_ARG(in_dtype == SOSWSOD_DTYPE_F32 || in_dtype == SOSWSOD_DTYPE_BF16, "colsum: bad dtype");
+    const int vec = in_dtype == SOSWSOD_DTYPE_BF16 ? 8 : 4;
+    const int esz = in_dtype == SOSWSOD_DTYPE_BF16 ? 2 : 4;
+    if (workspace && cols % vec == 0 && ((ld_in * esz) & 15) == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0 &&
+        (reinterpret_cast<uintptr_t>(workspace) & 15) == 0) {
+        const int chunks = colsum_chunks(rows, cols, vec);
+        if (workspace_bytes >= (size_t)chunks * cols * 4 && chunks > 1) {
+            const int rows_per_chunk = (rows + chunks - 1) / chunks;
+            const dim3 grid((cols / vec + 127) / 128, chunks);
+            if (in_dtype == SOSWSOD_DTYPE_BF16)
+                colsum_partial_kernel<__nv_bfloat16, 8><<<grid, 128, 0, (cudaStream_t)stream>>>(
+                    (const __nv_bfloat16*)in, ld_in, rows, cols, rows_per_chunk, (float*)workspace);
+            else
+                colsum_partial_kernel<float, 4><<<grid, 128, 0, (cudaStream_t)stream>>>((const float*)in, ld_in, rows, cols,
+                                                                                     rows_per_chunk, (float*)workspace);
+            SOSWSOD_CHECK_LAUNCH();
+            colsum_final_kernel<<<(cols + 255) / 256, 256, 0, (cudaStream_t)stream>>>((const float*)workspace, chunks, cols, out);
+            SOSWSOD_CHECK_LAUNCH();
+            return SOSWSOD_OK;
+        }
+    }
     const int grid = (cols + 31) / 32;
     if (in_dtype == SOSWSOD_DTYPE_BF16)
         colsum_kernel<__nv_bfloat16><<<grid, 1024, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)in, ld_in, rows, cols, out);

@@ -9,6 +9,8 @@
 // semantics given identical fp32 scores: IoU uses explicit round-to-nearest mul/add/sub/div (no FMA),
 // thresholds are compared in fp32, max over seeds keeps the first maximum, ordering is
 // (score desc, index asc).  Reference lines are cited per kernel.
+#include <cooperative_groups.h>
+
 #include "common.cuh"
 
 namespace soswsod {
@@ -255,8 +257,10 @@ oicr_nms_label_kernel(unsigned long long* __restrict__ cand_key, const int32_t* 
 //   the branch loss is the mean over the V views (roi_heads_oicrplus.py:384-388); with flip_quirk the last
 //   view's loss is evaluated on view V-2's predictions (:381).
 // -------------------------------------------------------------------------------------------------
+constexpr int kLossCluster = 8;   // CTAs (row slices) per (logit view, branch); partial sums meet in rank order over DSMEM
+
 template <int CJ>
-__global__ void __launch_bounds__(kOicrThreads)
+__global__ void __cluster_dims__(kLossCluster, 1, 1) __launch_bounds__(kOicrThreads)
 oicr_loss_kernel(const float* __restrict__ logits, long long ld, int col_ref0, int ref_stride,
                  const float* __restrict__ boxes, const int32_t* __restrict__ gt_class,
                  const float* __restrict__ gt_weight, const int32_t* __restrict__ gt_index, int V, int R, int C,
@@ -264,8 +268,14 @@ oicr_loss_kernel(const float* __restrict__ logits, long long ld, int col_ref0, i
                  int32_t* __restrict__ acc_counts, float* __restrict__ dlogits, long long ld_d) {
     __shared__ float s_loss[32][4];
     __shared__ int s_acc[32][4];
-    const int u = blockIdx.x, k = blockIdx.y;
+    __shared__ float s_part[4];   // this CTA's (ce, box0, box1) -- read by rank 0 of the cluster
+    __shared__ int s_parti[4];
+    cooperative_groups::cluster_group cluster = cooperative_groups::this_cluster();
+    const int rank = (int)cluster.block_rank();
+    const int u = blockIdx.x / kLossCluster, k = blockIdx.y;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int rows_per = (R + kLossCluster - 1) / kLossCluster;
+    const int r_lo = min(rank * rows_per, R), r_hi = min(r_lo + rows_per, R);
     const int C1 = C + 1;
     const int col = col_ref0 + k * ref_stride;
     const bool quirk = flip_quirk && V >= 2;
@@ -288,7 +298,7 @@ oicr_loss_kernel(const float* __restrict__ logits, long long ld, int col_ref0, i
     float box_sum[2] = {0.f, 0.f};
     int n_fg = 0, n_acc = 0, n_fgacc = 0, n_fn = 0;
 
-    for (int r = warp; r < R; r += 32) {
+    for (int r = r_lo + warp; r < r_hi; r += 32) {
         const float* zrow = logits + ((size_t)u * R + r) * ld + col;
         const int y = yk[r];
         const float w = (y == -1) ? 0.f : wk[r];
@@ -379,12 +389,25 @@ oicr_loss_kernel(const float* __restrict__ logits, long long ld, int col_ref0, i
         s_acc[warp][0] = n_fg; s_acc[warp][1] = n_acc; s_acc[warp][2] = n_fgacc; s_acc[warp][3] = n_fn;
     }
     __syncthreads();
-    if (threadIdx.x == 0 && nlv > 0) {
+    if (threadIdx.x == 0) {
         float ce = 0.f, b0 = 0.f, b1 = 0.f;
         int a0 = 0, a1 = 0, a2 = 0, a3 = 0;
         for (int wi = 0; wi < 32; ++wi) {
             ce += s_loss[wi][0]; b0 += s_loss[wi][1]; b1 += s_loss[wi][2];
             a0 += s_acc[wi][0]; a1 += s_acc[wi][1]; a2 += s_acc[wi][2]; a3 += s_acc[wi][3];
+        }
+        s_part[0] = ce; s_part[1] = b0; s_part[2] = b1;
+        s_parti[0] = a0; s_parti[1] = a1; s_parti[2] = a2; s_parti[3] = a3;
+    }
+    cluster.sync();
+    if (threadIdx.x == 0 && nlv > 0 && rank == 0) {
+        float ce = 0.f, b0 = 0.f, b1 = 0.f;
+        int a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+        for (int q = 0; q < kLossCluster; ++q) {
+            const float* pf = cluster.map_shared_rank(&s_part[0], q);
+            const int* pi = cluster.map_shared_rank(&s_parti[0], q);
+            ce += pf[0]; b0 += pf[1]; b1 += pf[2];
+            a0 += pi[0]; a1 += pi[1]; a2 += pi[2]; a3 += pi[3];
         }
         for (int t = 0; t < nlv; ++t) {
             const int v = lv[t];
@@ -396,6 +419,7 @@ oicr_loss_kernel(const float* __restrict__ logits, long long ld, int col_ref0, i
             }
         }
     }
+    cluster.sync();   // rank 0 has read every peer's partials before any CTA of the cluster exits
 }
 
 __global__ void oicr_finalize_kernel(const float* __restrict__ view_losses, int V, int K, float* __restrict__ losses) {
@@ -481,7 +505,7 @@ extern "C" int soswsod_oicr_loss(const float* logits, long long ld, int col_ref0
     SOSWSOD_CHECK_ARG(C + 1 <= 32 * kMaxCJ, "oicr_loss: C=%d unsupported", C);
     SOSWSOD_CHECK_ARG(col_ref0 >= 0 && col_ref0 + (long long)(K - 1) * ref_stride + 5 * C + 1 <= ld, "oicr_loss: columns exceed ld");
     cudaStream_t st = (cudaStream_t)stream;
-    dim3 grid(num_views, K);
+    dim3 grid(num_views * kLossCluster, K);
     const int cj = (C + 1 + 31) / 32;
 #define LAUNCH(CJ) oicr_loss_kernel<CJ><<<grid, kOicrThreads, 0, st>>>(logits, ld, col_ref0, ref_stride, boxes, gt_class, gt_weight, gt_index, num_views, R, C, flip_quirk, wx, wy, ww, wh, view_losses, acc_counts, dlogits, ld_d)
     switch (cj) { case 1: LAUNCH(1); break; case 2: LAUNCH(2); break; case 3: LAUNCH(3); break; default: LAUNCH(4); break; }

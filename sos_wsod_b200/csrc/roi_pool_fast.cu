@@ -32,11 +32,13 @@ roi_plan_kernel(const float* __restrict__ rois, int R, int n, int H, int W, floa
     int* order = reinterpret_cast<int*>(plan + kPlanHeaderBytes);
     RoiRecord* rec = reinterpret_cast<RoiRecord*>(plan + plan_records_offset(R));
 
-    // rois of earlier images (start of this image's segment) and of this image
+    // one CTA per (image, chunk of 1024 rois): position of the chunk's first roi of this image inside `order` =
+    // rois of earlier images + rois of this image in earlier chunks
+    const int r_chunk = blockIdx.y * kPlanThreads;
     int before = 0, mine = 0;
     for (int r = threadIdx.x; r < R; r += kPlanThreads) {
         const int rb = (int)rois[(size_t)r * 5];
-        before += (rb >= 0 && rb < b) ? 1 : 0;
+        before += ((rb >= 0 && rb < b) || (rb == b && r < r_chunk)) ? 1 : 0;
         mine += (rb == b) ? 1 : 0;
     }
     before = warp_sum_int(before);
@@ -48,26 +50,21 @@ roi_plan_kernel(const float* __restrict__ rois, int R, int n, int H, int W, floa
         atomicAdd(&s_base[1], mine);
     }
     __syncthreads();
-    const int start = s_base[0];
-    if (threadIdx.x == 0) {
-        img_start[b] = start;
-        if (b == n - 1) img_start[n] = start + s_base[1];
+    const int base = s_base[0];
+    if (threadIdx.x == 0 && blockIdx.y == 0) {
+        img_start[b] = base;
+        if (b == n - 1) img_start[n] = base + s_base[1];
     }
-    // stable compaction of this image's roi indices + the records
-    int base = start;
-    for (int r0 = 0; r0 < R; r0 += kPlanThreads) {
-        const int r = r0 + threadIdx.x;
+    // stable compaction of this chunk's rois of image b + their records
+    {
+        const int r = r_chunk + threadIdx.x;
         bool flag = false;
         if (r < R) flag = ((int)rois[(size_t)r * 5] == b);
         const unsigned bal = __ballot_sync(FULL_MASK, flag);
         if (lane == 0) s_warp[warp] = __popc(bal);
         __syncthreads();
-        int wpre = 0, tot = 0;
-        for (int i = 0; i < 32; ++i) {
-            const int c = s_warp[i];
-            wpre += (i < warp) ? c : 0;
-            tot += c;
-        }
+        int wpre = 0;
+        for (int i = 0; i < warp; ++i) wpre += s_warp[i];
         if (flag) {
             order[base + wpre + __popc(bal & ((1u << lane) - 1u))] = r;
             const RoiGeom g = roi_geometry(rois + (size_t)r * 5, spatial_scale, kPlanP, kPlanP);
@@ -96,14 +93,12 @@ roi_plan_kernel(const float* __restrict__ rois, int R, int n, int H, int W, floa
                 d4[3] = make_uint4(0u, 0u, 0xFFFF0202u, 0u);
             }
         }
-        base += tot;
-        __syncthreads();
     }
 }
 
 int launch_roi_plan(const float* rois, int R, int n, int h, int w, float scale, const float* row_scale, float bias,
                     void* plan, cudaStream_t st) {
-    roi_plan_kernel<<<n, kPlanThreads, 0, st>>>(rois, R, n, h, w, scale, row_scale, bias, static_cast<uint8_t*>(plan));
+    roi_plan_kernel<<<dim3(n, (R + kPlanThreads - 1) / kPlanThreads), kPlanThreads, 0, st>>>(rois, R, n, h, w, scale, row_scale, bias, static_cast<uint8_t*>(plan));
     SOSWSOD_CHECK_LAUNCH();
     return SOSWSOD_OK;
 }

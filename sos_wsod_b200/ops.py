@@ -221,8 +221,11 @@ def colsum(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     rows, cols = x.shape
     if out is None:
         out = torch.empty((cols,), dtype=torch.float32, device=x.device)
-    check(_lib.load().soswsod_colsum(_ptr(x), _dt(x), x.stride(0), rows, cols, _ptr(out), _stream()), "colsum")
-    _count(1)
+    lib = _lib.load()
+    nbytes = lib.soswsod_colsum_workspace_bytes(rows, cols, _dt(x))
+    ws = torch.empty((nbytes,), dtype=torch.uint8, device=x.device) if nbytes else None
+    check(lib.soswsod_colsum(_ptr(x), _dt(x), x.stride(0), rows, cols, _ptr(out), _ptr(ws), nbytes, _stream()), "colsum")
+    _count(2 if nbytes else 1)
     return out
 
 

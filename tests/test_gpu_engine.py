@@ -151,6 +151,53 @@ def test_tta_detect_matches_oracle(cuda_lib):
     assert torch.equal(dr[:n].cpu().long(), e[3]) and torch.equal(ds[:n].cpu(), e[1])
 
 
+def test_detection_result_generation_pipeline(cuda_lib, tmp_path):
+    """BASELINE configs[4] in miniature: images sharded like InferenceSampler, TTA views through the engine, merged
+    scores/boxes -> threshold -> per-class NMS -> top-k on the device, rows through the VOC writer.  The json must be
+    exactly what the ORACLE's writer makes of the oracle's inference on the engine's merged fp32 scores / boxes."""
+    import json
+
+    from oracle import eval_ref
+    from sos_wsod_b200.evaluation import PascalVOCDetectionWriter, generate_detection_results, inference_shard
+    from sos_wsod_b200.modeling.fast_rcnn_oicr import _detections_to_instances
+
+    n_img, world = 5, 2
+    setups = [_small_setup(R=150, seed=20 + i) for i in range(n_img)]
+    cfg = setups[0][5]
+    C = cfg.num_classes
+    expected = []
+
+    def make_detect(collect):
+        def detect(i):
+            eng, vb, views, p, gt_classes, _ = setups[i]
+            (h1, w1), (h2, w2) = views[0].image_size, views[2].image_size
+            tf = [(1.0, 1.0, False, float(w1)), (1.0, 1.0, True, float(w1)), (w1 / w2, h1 / h2, False, float(w2)),
+                  (w1 / w2, h1 / h2, True, float(w2))]
+            det, acc_p, acc_b = eng.tta_detect(vb, tf, (h1, w1))
+            inst, _ = _detections_to_instances(det, (h1, w1))
+            if collect:
+                e = ref.fast_rcnn_inference_single_image(acc_b.cpu(), acc_p.cpu(), (h1, w1), cfg.score_thresh_test,
+                                                         cfg.nms_thresh_test, cfg.detections_per_image)
+                expected.append({"image_id": 100 + i, "boxes": e[0].numpy(), "scores": e[1].tolist(), "classes": e[2].tolist()})
+            return {"image_id": 100 + i, "instances": inst[0]}
+        return detect
+
+    names = [f"c{k}" for k in range(C)]
+    w_all = PascalVOCDetectionWriter("voc_2007_test", names, str(tmp_path / "all_{}.json"))
+    assert list(generate_detection_results(make_detect(True), n_img, w_all)) == list(range(n_img))
+    text = open(w_all.save()).read()
+    assert text == eval_ref.voc_json_text(expected, C)
+    rows = json.loads(text)
+    assert 0 < len(rows) <= n_img * cfg.detections_per_image
+    # the two InferenceSampler blocks, written separately and merged in rank order, give the same file
+    parts = []
+    for r in range(world):
+        w = PascalVOCDetectionWriter("voc_2007_test", names, str(tmp_path / f"r{r}_{{}}.json"))
+        assert list(generate_detection_results(make_detect(False), n_img, w, r, world)) == list(inference_shard(n_img, r, world))
+        parts.append(dict(w._predictions))
+    assert json.dumps(w_all.rows(parts)) == text
+
+
 def test_plugin_surface_train_and_eval(cuda_lib):
     """OICRPlusHeads built from config through the registry: forward(images, features, proposals, targets) returns
     the reference's loss keys, backward fills .grad of every parameter with the engine's gradients, eval returns
