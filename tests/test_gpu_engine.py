@@ -47,11 +47,12 @@ def _rel_err(a, b):
     return (a - b).norm().item() / max(b.norm().item(), 1e-30)
 
 
-@pytest.mark.parametrize("dropout", [0.0, 0.5])
-def test_train_step_matches_oracle(cuda_lib, dropout):
+@pytest.mark.parametrize("dropout,C,K", [(0.0, 20, 3), (0.5, 20, 3), (0.0, 80, 3), (0.5, 20, 4)])
+def test_train_step_matches_oracle(cuda_lib, dropout, C, K):
+    """VOC shape (C=20, K=3: BASELINE configs[1]), COCO shape (C=80: configs[3]) and the shipped K=4 yaml."""
     from sos_wsod_b200 import ops
 
-    eng, vb, views, p, gt_classes, cfg = _small_setup()
+    eng, vb, views, p, gt_classes, cfg = _small_setup(C=C, K=K)
     cfg.dropout_p = dropout
     R, C, K, V = vb.R, cfg.num_classes, cfg.refine_k, 4
     gt_int = torch.unique(gt_classes)
