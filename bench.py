@@ -248,6 +248,10 @@ def run_b200_arm(args):
     dev = torch.device("cuda", local_rank)
     _lib.load()
     if world > 1:
+        # stdout carries ONE json line: NCCL prints its version banner there at any debug level >= VERSION
+        os.environ.pop("NCCL_DEBUG", None)
+        if "SOSWSOD_NCCL_DEBUG" in os.environ:
+            os.environ["NCCL_DEBUG"] = os.environ["SOSWSOD_NCCL_DEBUG"]
         dist.init_process_group("nccl", device_id=dev)
     peaks = _peaks()
 
@@ -290,6 +294,26 @@ def run_b200_arm(args):
         return out
 
     ops.gemm_bf16 = timed_gemm
+
+    # ---- the ROI-pool kernels, timed the same way (secondary roofline: HBM-side compulsory bytes / duration) ----
+    roi_events = {"fwd": [], "bwd": []}
+    orig_fwd, orig_bwd = ops.roi_pool_forward, ops.roi_pool_backward
+
+    def timed_roi(kind, orig):
+        def fn(*a, **kw):
+            if not record_gemm["on"]:
+                return orig(*a, **kw)
+            e0 = torch.cuda.Event(enable_timing=True)
+            e1 = torch.cuda.Event(enable_timing=True)
+            e0.record()
+            out = orig(*a, **kw)
+            e1.record()
+            roi_events[kind].append((e0, e1))
+            return out
+        return fn
+
+    ops.roi_pool_forward = timed_roi("fwd", orig_fwd)
+    ops.roi_pool_backward = timed_roi("bwd", orig_bwd)
 
     def device_step(i):
         im = dev_imgs[i % n_img]
@@ -365,6 +389,24 @@ def run_b200_arm(args):
                 "traffic": traffic, "traffic_unit": "DRAM bytes per launch (avg over the step's GEMM launches)",
                 "traffic_source": traffic_src, "algorithmic_bytes_per_launch": alg_bytes,
                 "gemm_share_of_step": tot_ms / ms, "fc6_fwd_tflops": fc6["tflops"], "detail": detail}
+
+    # ROI pool: per step 2 forward + 2 backward launches (one per scale pair).  Compulsory HBM bytes per step:
+    # forward = conv5 planes in + (bf16 operand + uint16 arg-max) out; backward = (bf16 grad + uint16 arg-max) in + fp32 planes out
+    plane_bytes = sum(2 * 512 * h * w * 4 for (h, w) in synth_views_sizes())
+    xa_bytes = VIEWS * R_PROPOSALS * 25088 * (2 + 2)
+    roi = {}
+    for kind in ("fwd", "bwd"):
+        tot = sum(e0.elapsed_time(e1) for e0, e1 in roi_events[kind])
+        n_l = max(len(roi_events[kind]), 1)
+        per_step_ms = tot / max(args.steps, 1)
+        roi[kind] = {"launches_per_step": len(roi_events[kind]) // max(args.steps, 1), "ms_per_step": per_step_ms,
+                     "avg_us_per_launch": 1e3 * tot / n_l,
+                     "compulsory_hbm_gbs": (plane_bytes + xa_bytes) / (per_step_ms * 1e-3) / 1e9 if per_step_ms > 0 else 0.0,
+                     "frac_of_hbm_peak": ((plane_bytes + xa_bytes) / (per_step_ms * 1e-3) / 1e9) / peaks["hbm_gbs"] if per_step_ms > 0 else 0.0}
+    roi["share_of_step"] = (roi["fwd"]["ms_per_step"] + roi["bwd"]["ms_per_step"]) / ms_per_step
+    roi["bound"] = "shared-memory gather / read-add-write inside the SM (planes staged in smem); HBM carries only the compulsory bytes"
+    roofline["roi_pool"] = roi
+    ops.roi_pool_forward, ops.roi_pool_backward = orig_fwd, orig_bwd
 
     # ---- end to end through the plugin surface, host buffers, H2D/D2H inside the timed region ----
     heads.grad_hook = grad_hook

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define SOSWSOD_ABI_VERSION 3
+#define SOSWSOD_ABI_VERSION 4
 
 #define SOSWSOD_OK 0
 #define SOSWSOD_ERR_INVALID (-1)     /* bad shape / null pointer / misalignment */
@@ -100,11 +100,16 @@ int soswsod_roi_pool_backward(const void* grad_out, int grad_dtype, long long ld
  *                       * (mask_src[m,n] > 0 ? mask_scale : 0) (if mask_src, bf16 [M, ld_mask]) ;
  *                       dropout keep/scale with a counter-based hash of (seed, m, n) (if dropout_p > 0)
  *   D: fp32 or bf16 per d_dtype.  lda/ldb multiples of 8 elements, bases 16-byte aligned.
+ *   sched_workspace: NULL (tiles statically interleaved over the persistent CTAs) or 8 bytes of device
+ *     memory, zeroed ONCE by the caller and reused by every launch on the same stream: the CTAs then take
+ *     tiles from a global counter (a CTA slowed by a co-resident kernel takes fewer), and the last CTA
+ *     re-arms the counter.  Launches that may run concurrently need separate workspaces.
  * ------------------------------------------------------------------------------------------- */
 int soswsod_gemm_bf16(const void* a, long long lda, int a_mn_major, const void* b, long long ldb,
                       int b_mn_major, void* d, long long ldd, int d_dtype, int m, int n, int k,
                       const float* bias, int relu, const void* mask_src, long long ld_mask, float mask_scale,
-                      float dropout_p, unsigned long long dropout_seed, soswsod_stream_t stream);
+                      float dropout_p, unsigned long long dropout_seed, void* sched_workspace,
+                      soswsod_stream_t stream);
 
 /* The dropout keep-mask the GEMM epilogue applies, materialised as uint8 [m, n] (1 = keep): lets a
  * test feed the identical mask to the oracle. */

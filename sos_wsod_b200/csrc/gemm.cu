@@ -31,7 +31,7 @@ constexpr int kNumAccStages = 2;
 __host__ __device__ constexpr int gemm_stages(int block_n) { return block_n == 256 ? 4 : 6; }
 __host__ __device__ constexpr int gemm_stage_bytes(int block_n) { return (kBlockM + block_n) * kBlockK * 2; }
 __host__ __device__ constexpr int gemm_smem_bytes(int block_n) {
-    return gemm_stages(block_n) * gemm_stage_bytes(block_n) + 1024 /*align slack*/ + 256 /*barriers*/;
+    return gemm_stages(block_n) * gemm_stage_bytes(block_n) + 1024 /*align slack*/ + 384 /*barriers, tile ring*/;
 }
 
 // ---- PTX wrappers (mbarrier / TMA ones live in tma.cuh) -------------------------------------------
@@ -106,7 +106,8 @@ struct GemmEpilogue {
 template <int BLOCK_N, bool A_MN, bool B_MN, bool OUT_BF16>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                 void* __restrict__ dptr, long long ldd, int M, int N, int K, GemmEpilogue ep) {
+                 void* __restrict__ dptr, long long ldd, int M, int N, int K, GemmEpilogue ep,
+                 unsigned int* __restrict__ sched) {
     constexpr int kStages = gemm_stages(BLOCK_N);
     constexpr int kABytes = kBlockM * kBlockK * 2;
     constexpr int kBBytes = BLOCK_N * kBlockK * 2;
@@ -125,6 +126,14 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     const uint32_t tmem_ptr_addr = bar_base + 8u * (2 * kStages + 2 * kNumAccStages);
     volatile uint32_t* tmem_ptr_generic =
         reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_ptr_addr - smem_u32(smem_raw)));
+    // tile scheduler: the producer publishes the tile index of every tile this CTA works on through a small ring
+    // (full / empty mbarriers); with a scheduler workspace the next index comes from a global counter, so CTAs that
+    // are slowed down (a co-resident NCCL kernel, a throttled SM) simply take fewer tiles.
+    constexpr int kSchedSlots = 4;
+    auto sfull_bar = [&](int s) { return tmem_ptr_addr + 8u + 8u * s; };
+    auto sempty_bar = [&](int s) { return tmem_ptr_addr + 8u + 8u * (kSchedSlots + s); };
+    const uint32_t sring_addr = tmem_ptr_addr + 8u + 8u * (2 * kSchedSlots);
+    volatile int* sring = reinterpret_cast<volatile int*>(smem_raw + (sring_addr - smem_u32(smem_raw)));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m_tiles = (M + kBlockM - 1) / kBlockM;
@@ -142,6 +151,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         for (int s = 0; s < kNumAccStages; ++s) {
             mbar_init(tfull_bar(s), 1);
             mbar_init(tempty_bar(s), 128);
+        }
+        for (int s = 0; s < kSchedSlots; ++s) {
+            mbar_init(sfull_bar(s), 1);
+            mbar_init(sempty_bar(s), 5);   // MMA lane + one lane of each epilogue warp
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -173,7 +186,18 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+            int ss = 0;
+            uint32_t sphase = 0;
+            int t = blockIdx.x;
+            while (true) {
+                mbar_wait(sempty_bar(ss), sphase ^ 1u);
+                sring[ss] = t;
+                mbar_arrive(sfull_bar(ss));
+                if (++ss == kSchedSlots) {
+                    ss = 0;
+                    sphase ^= 1u;
+                }
+                if (t >= num_tiles) break;
                 int mb, nb;
                 tile_coords(t, mb, nb);
                 const int m0 = mb * kBlockM, n0 = nb * BLOCK_N;
@@ -202,6 +226,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                         phase ^= 1u;
                     }
                 }
+                t = sched ? (int)(gridDim.x + atomicAdd(&sched[0], 1u)) : t + (int)gridDim.x;
             }
         }
     } else if (warp == 1) {
@@ -217,7 +242,17 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             uint32_t phase = 0;
             int as = 0;
             uint32_t aphase = 0;
-            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+            int ss = 0;
+            uint32_t sphase = 0;
+            while (true) {
+                mbar_wait(sfull_bar(ss), sphase);
+                const int t = sring[ss];
+                mbar_arrive(sempty_bar(ss));
+                if (++ss == kSchedSlots) {
+                    ss = 0;
+                    sphase ^= 1u;
+                }
+                if (t >= num_tiles) break;
                 mbar_wait(tempty_bar(as), aphase ^ 1u);
                 tcgen05_fence_after();
                 const uint32_t tmem_d = tmem_base + (uint32_t)(as * BLOCK_N);
@@ -252,7 +287,18 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         const float drop_scale = ep.dropout_p > 0.f ? 1.0f / (1.0f - ep.dropout_p) : 1.0f;
         int as = 0;
         uint32_t aphase = 0;
-        for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        int ss = 0;
+        uint32_t sphase = 0;
+        while (true) {
+            mbar_wait(sfull_bar(ss), sphase);
+            const int t = sring[ss];
+            __syncwarp();
+            if (lane == 0) mbar_arrive(sempty_bar(ss));
+            if (++ss == kSchedSlots) {
+                ss = 0;
+                sphase ^= 1u;
+            }
+            if (t >= num_tiles) break;
             int mb, nb;
             tile_coords(t, mb, nb);
             const int row = mb * kBlockM + q * 32 + lane;
@@ -368,6 +414,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         tcgen05_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols) : "memory");
     }
+    // the last CTA to leave re-arms the scheduler workspace for the next launch on this stream
+    if (sched && threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(&sched[1], 1u) == gridDim.x - 1) {
+            sched[0] = 0u;
+            sched[1] = 0u;
+            __threadfence();
+        }
+    }
 }
 
 // ---- host side -------------------------------------------------------------------------------------
@@ -375,24 +430,24 @@ int device_num_sms();
 
 template <int BLOCK_N, bool A_MN, bool B_MN, bool OUT_BF16>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, void* d, long long ldd, int m, int n, int k,
-                       const GemmEpilogue& ep, cudaStream_t st) {
+                       const GemmEpilogue& ep, unsigned int* sched, cudaStream_t st) {
     auto kern = gemm_bf16_kernel<BLOCK_N, A_MN, B_MN, OUT_BF16>;
     const int smem = gemm_smem_bytes(BLOCK_N);
     SOSWSOD_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     const int tiles = ((m + kBlockM - 1) / kBlockM) * ((n + BLOCK_N - 1) / BLOCK_N);
     const int grid = tiles < device_num_sms() ? tiles : device_num_sms();
-    kern<<<grid, kGemmThreads, smem, st>>>(ta, tb, d, ldd, m, n, k, ep);
+    kern<<<grid, kGemmThreads, smem, st>>>(ta, tb, d, ldd, m, n, k, ep, sched);
     SOSWSOD_CHECK_LAUNCH();
     return SOSWSOD_OK;
 }
 
 template <int BLOCK_N, bool OUT_BF16>
 static int dispatch_major(int a_mn, int b_mn, const CUtensorMap& ta, const CUtensorMap& tb, void* d, long long ldd, int m,
-                          int n, int k, const GemmEpilogue& ep, cudaStream_t st) {
-    if (!a_mn && !b_mn) return launch_gemm<BLOCK_N, false, false, OUT_BF16>(ta, tb, d, ldd, m, n, k, ep, st);
-    if (!a_mn && b_mn) return launch_gemm<BLOCK_N, false, true, OUT_BF16>(ta, tb, d, ldd, m, n, k, ep, st);
-    if (a_mn && !b_mn) return launch_gemm<BLOCK_N, true, false, OUT_BF16>(ta, tb, d, ldd, m, n, k, ep, st);
-    return launch_gemm<BLOCK_N, true, true, OUT_BF16>(ta, tb, d, ldd, m, n, k, ep, st);
+                          int n, int k, const GemmEpilogue& ep, unsigned int* sched, cudaStream_t st) {
+    if (!a_mn && !b_mn) return launch_gemm<BLOCK_N, false, false, OUT_BF16>(ta, tb, d, ldd, m, n, k, ep, sched, st);
+    if (!a_mn && b_mn) return launch_gemm<BLOCK_N, false, true, OUT_BF16>(ta, tb, d, ldd, m, n, k, ep, sched, st);
+    if (a_mn && !b_mn) return launch_gemm<BLOCK_N, true, false, OUT_BF16>(ta, tb, d, ldd, m, n, k, ep, sched, st);
+    return launch_gemm<BLOCK_N, true, true, OUT_BF16>(ta, tb, d, ldd, m, n, k, ep, sched, st);
 }
 
 }  // namespace soswsod
@@ -403,8 +458,10 @@ extern "C" int soswsod_gemm_bf16(const void* a, long long lda, int a_mn_major, c
                                  int b_mn_major, void* d, long long ldd, int d_dtype, int m, int n, int k,
                                  const float* bias, int relu, const void* mask_src, long long ld_mask,
                                  float mask_scale, float dropout_p, unsigned long long dropout_seed,
-                                 soswsod_stream_t stream) {
+                                 void* sched_workspace, soswsod_stream_t stream) {
     SOSWSOD_CHECK_ARG(a && b && d, "gemm_bf16: null pointer");
+    SOSWSOD_CHECK_ARG(((uintptr_t)sched_workspace & 7) == 0, "gemm_bf16: scheduler workspace must be 8-byte aligned");
+    unsigned int* sched = reinterpret_cast<unsigned int*>(sched_workspace);
     SOSWSOD_CHECK_ARG(m > 0 && n > 0 && k > 0, "gemm_bf16: bad shape m=%d n=%d k=%d", m, n, k);
     SOSWSOD_CHECK_ARG(d_dtype == SOSWSOD_DTYPE_F32 || d_dtype == SOSWSOD_DTYPE_BF16, "gemm_bf16: bad d_dtype");
     SOSWSOD_CHECK_ARG((lda % 8) == 0 && (ldb % 8) == 0, "gemm_bf16: lda/ldb must be multiples of 8 elements");
@@ -434,11 +491,11 @@ extern "C" int soswsod_gemm_bf16(const void* a, long long lda, int a_mn_major, c
     ep.dropout_seed = dropout_seed;
     const bool obf = d_dtype == SOSWSOD_DTYPE_BF16;
     if (block_n == 256) {
-        if (obf) return dispatch_major<256, true>(a_mn_major, b_mn_major, ta, tb, d, ldd, m, n, k, ep, st);
-        return dispatch_major<256, false>(a_mn_major, b_mn_major, ta, tb, d, ldd, m, n, k, ep, st);
+        if (obf) return dispatch_major<256, true>(a_mn_major, b_mn_major, ta, tb, d, ldd, m, n, k, ep, sched, st);
+        return dispatch_major<256, false>(a_mn_major, b_mn_major, ta, tb, d, ldd, m, n, k, ep, sched, st);
     }
-    if (obf) return dispatch_major<128, true>(a_mn_major, b_mn_major, ta, tb, d, ldd, m, n, k, ep, st);
-    return dispatch_major<128, false>(a_mn_major, b_mn_major, ta, tb, d, ldd, m, n, k, ep, st);
+    if (obf) return dispatch_major<128, true>(a_mn_major, b_mn_major, ta, tb, d, ldd, m, n, k, ep, sched, st);
+    return dispatch_major<128, false>(a_mn_major, b_mn_major, ta, tb, d, ldd, m, n, k, ep, sched, st);
 }
 
 namespace soswsod {

@@ -137,6 +137,20 @@ def roi_pool_backward(grad_out: torch.Tensor, argmax: torch.Tensor, rois: torch.
 # ------------------------------------------------------------------------------------------------
 # (2) GEMM + helpers
 # ------------------------------------------------------------------------------------------------
+_GEMM_SCHED = {}
+
+
+def _gemm_sched(device) -> torch.Tensor:
+    """The GEMM's dynamic tile-scheduler workspace (8 bytes, zeroed once, re-armed by the kernel) of the current
+    stream: launches on one stream are ordered and share it, other streams get their own."""
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    t = _GEMM_SCHED.get(key)
+    if t is None:
+        t = torch.zeros(2, dtype=torch.int32, device=device)
+        _GEMM_SCHED[key] = t
+    return t
+
+
 def gemm_bf16(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool = False,
               out_dtype: torch.dtype = torch.float32, bias: Optional[torch.Tensor] = None, relu: bool = False,
               mask_src: Optional[torch.Tensor] = None, mask_scale: float = 1.0, dropout_p: float = 0.0,
@@ -167,7 +181,8 @@ def gemm_bf16(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: boo
     lib = _lib.load()
     check(lib.soswsod_gemm_bf16(_ptr(a), a.stride(0), int(a_mn), _ptr(b), b.stride(0), int(b_mn), _ptr(out),
                                 out.stride(0), _dt(out), m, n, k, _ptr(bias), int(relu), _ptr(mask_src), ld_mask,
-                                float(mask_scale), float(dropout_p), int(dropout_seed) & 0xFFFFFFFFFFFFFFFF, _stream()),
+                                float(mask_scale), float(dropout_p), int(dropout_seed) & 0xFFFFFFFFFFFFFFFF,
+                                _ptr(_gemm_sched(a.device)), _stream()),
           "gemm_bf16")
     _count(1)
     return out
