@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define SOSWSOD_ABI_VERSION 4
+#define SOSWSOD_ABI_VERSION 5
 
 #define SOSWSOD_OK 0
 #define SOSWSOD_ERR_INVALID (-1)     /* bad shape / null pointer / misalignment */
@@ -163,6 +163,13 @@ int soswsod_oicr_avg_scores(const float* wsddn_scores, const float* logits, long
                             int ref_stride, int num_views, int R, int C, int K, float* prev,
                             soswsod_stream_t stream);
 
+/* soswsod_image_level_gt: get_image_level_gt (W/modeling/roi_heads/roi_heads.py:144-164) on the device:
+ *   gt_classes int64 / int32 [n] (any order, duplicates allowed) -> gt_list int32 [C] = the distinct classes
+ *   ascending, padded with -1; gt_count int32 [1]; gt_onehot fp32 [C].  C <= 128.  No host synchronisation
+ *   (torch.unique, which the reference calls, reads its output size back). */
+int soswsod_image_level_gt(const void* gt_classes, int is_int64, int n, int C, int32_t* gt_list, int32_t* gt_count,
+                           float* gt_onehot, soswsod_stream_t stream);
+
 /* soswsod_oicr_mine_label: pseudo-GT mining + proposal labelling for all K branches.
  *   Replaces get_pgt_top_k / get_pgt_mist (roi_heads_oicrplus.py:559-757: per-GT-class top-k,
  *   threshold with rank 0 forced, class-agnostic NMS at `nms_thr`), pairwise_iou
@@ -173,6 +180,9 @@ int soswsod_oicr_avg_scores(const float* wsddn_scores, const float* logits, long
  *   prev      fp32 [K, R, ld_prev]; only the gt_classes columns are read
  *   boxes     fp32 [R, 4]  view-1 proposal boxes
  *   gt_classes int32 [G] sorted ascending, G >= 1
+ *   gt_count  NULL, or a DEVICE int32: only the first *gt_count entries of gt_classes are live (G is then
+ *             the capacity, e.g. C) -- lets the caller keep the image-level labels on the device
+ *             (soswsod_image_level_gt) instead of reading torch.unique's size back to the host
  *   top_k = max(int(R * WSL.MIST_P), 1) computed by the caller with the reference's Python arithmetic
  *           (roi_heads_oicrplus.py:657-662); score_thr/nms_thr = WSL.MIST_THRE (0.05) / 0.01
  *   iou_lo/iou_hi = MODEL.ROI_HEADS.IOU_THRESHOLDS (0.5, 0.6): <lo background, [lo,hi) ignore, >=hi fg
@@ -186,7 +196,7 @@ int soswsod_oicr_avg_scores(const float* wsddn_scores, const float* logits, long
  * ------------------------------------------------------------------------------------------- */
 size_t soswsod_oicr_mine_workspace_bytes(int top_k, int G, int K);
 int soswsod_oicr_mine_label(const float* prev, long long ld_prev, const float* boxes, const int32_t* gt_classes,
-                            int G, int R, int C, int K, int top_k, float score_thr, float nms_thr,
+                            int G, const int32_t* gt_count, int R, int C, int K, int top_k, float score_thr, float nms_thr,
                             float iou_lo, float iou_hi, int32_t* seed_count, int32_t* seed_index,
                             int32_t* seed_class, float* seed_score, int32_t* gt_class, float* gt_weight,
                             int32_t* gt_index, int32_t* counts, void* workspace, size_t workspace_bytes,

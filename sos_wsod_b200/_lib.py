@@ -10,7 +10,7 @@ from ctypes import c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_longl
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libsoswsod_b200.so")
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 DTYPE_F32, DTYPE_BF16 = 0, 1
 ARGMAX_I32, ARGMAX_U16 = 0, 1
@@ -38,7 +38,8 @@ SIGNATURES = {
     "soswsod_wsddn_forward": (c_int, [_P, _LL, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P, _LL, _P]),
     "soswsod_oicr_avg_scores": (c_int, [_P, _P, _LL, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P]),
     "soswsod_oicr_mine_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
-    "soswsod_oicr_mine_label": (c_int, [_P, _LL, _P, _P, c_int, c_int, c_int, c_int, c_int, c_float, c_float, c_float,
+    "soswsod_image_level_gt": (c_int, [_P, c_int, c_int, c_int, _P, _P, _P, _P]),
+    "soswsod_oicr_mine_label": (c_int, [_P, _LL, _P, _P, c_int, _P, c_int, c_int, c_int, c_int, c_float, c_float, c_float,
                                          c_float, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_size_t, _P]),
     "soswsod_oicr_loss": (c_int, [_P, _LL, c_int, c_int, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_float,
                                    c_float, c_float, c_float, _P, _P, _P, _P, _LL, _P]),

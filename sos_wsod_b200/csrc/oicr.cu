@@ -86,10 +86,17 @@ oicr_avg_scores_kernel(const float* __restrict__ wsddn_scores, const float* __re
 // -------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kOicrThreads)
 oicr_topk_kernel(const float* __restrict__ prev, long long ld_prev, const int32_t* __restrict__ gt_classes, int G,
-                 int R, int kt, float score_thr, int n_pow2, unsigned long long* __restrict__ cand_key,
-                 int32_t* __restrict__ cand_row) {
+                 const int32_t* __restrict__ gt_count, int R, int kt, float score_thr, int n_pow2,
+                 unsigned long long* __restrict__ cand_key, int32_t* __restrict__ cand_row) {
     extern __shared__ __align__(16) unsigned long long keys[];
     const int g = blockIdx.x, k = blockIdx.y;
+    // G is the capacity of gt_classes; with a device-side count only the first *gt_count entries are live (the
+    // slots of the others stay empty -- candidate order is rank-major then g either way)
+    if (gt_count && g >= *gt_count) {
+        unsigned long long* ck0 = cand_key + (size_t)k * kt * G;
+        for (int i = threadIdx.x; i < kt; i += blockDim.x) ck0[(size_t)i * G + g] = 0ull;
+        return;
+    }
     const int cls = gt_classes[g];
     const float* col = prev + (size_t)k * R * ld_prev + cls;
     for (int r = threadIdx.x; r < n_pow2; r += blockDim.x) {
@@ -451,13 +458,61 @@ extern "C" int soswsod_oicr_avg_scores(const float* wsddn_scores, const float* l
     return SOSWSOD_OK;
 }
 
+namespace soswsod {
+// get_image_level_gt (wsl/modeling/roi_heads/roi_heads.py:144-164) without the host round trip of torch.unique:
+// sorted distinct classes (padded to C with -1), their count and the one-hot row, all left on the device.
+template <typename T>
+__global__ void __launch_bounds__(128)
+image_level_gt_kernel(const T* __restrict__ gt, int n, int C, int32_t* __restrict__ list, int32_t* __restrict__ count,
+                      float* __restrict__ onehot) {
+    __shared__ int present[128];
+    __shared__ int wtot[4];
+    const int c = threadIdx.x;
+    present[c] = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += 128) {
+        const long long v = (long long)gt[i];
+        if (v >= 0 && v < C) present[(int)v] = 1;   // benign race: every writer stores 1
+    }
+    __syncthreads();
+    const bool on = c < C && present[c];
+    const unsigned bal = __ballot_sync(FULL_MASK, on);
+    if ((c & 31) == 0) wtot[c >> 5] = __popc(bal);
+    __syncthreads();
+    int before = __popc(bal & ((1u << (c & 31)) - 1u));
+    for (int w = 0; w < (c >> 5); ++w) before += wtot[w];
+    const int total = wtot[0] + wtot[1] + wtot[2] + wtot[3];
+    if (c < C) {
+        onehot[c] = on ? 1.f : 0.f;
+        if (on) list[before] = c;
+        if (c >= total) list[c] = -1;
+    }
+    if (c == 0) *count = total;
+}
+}  // namespace soswsod
+
+extern "C" int soswsod_image_level_gt(const void* gt_classes, int is_int64, int n, int C, int32_t* gt_list,
+                                      int32_t* gt_count, float* gt_onehot, soswsod_stream_t stream) {
+    SOSWSOD_CHECK_ARG(gt_list && gt_count && gt_onehot && (gt_classes || n == 0), "image_level_gt: null pointer");
+    SOSWSOD_CHECK_ARG(n >= 0 && C > 0 && C <= 128, "image_level_gt: need 0 < C <= 128");
+    if (is_int64)
+        image_level_gt_kernel<long long><<<1, 128, 0, (cudaStream_t)stream>>>((const long long*)gt_classes, n, C, gt_list,
+                                                                             gt_count, gt_onehot);
+    else
+        image_level_gt_kernel<int32_t><<<1, 128, 0, (cudaStream_t)stream>>>((const int32_t*)gt_classes, n, C, gt_list,
+                                                                           gt_count, gt_onehot);
+    SOSWSOD_CHECK_LAUNCH();
+    return SOSWSOD_OK;
+}
+
 extern "C" size_t soswsod_oicr_mine_workspace_bytes(int top_k, int G, int K) {
     const size_t m0 = (size_t)top_k * G;
     return (size_t)K * m0 * (8 + 4) + 256;
 }
 
 extern "C" int soswsod_oicr_mine_label(const float* prev, long long ld_prev, const float* boxes,
-                                       const int32_t* gt_classes, int G, int R, int C, int K, int top_k,
+                                       const int32_t* gt_classes, int G, const int32_t* gt_count, int R, int C, int K,
+                                       int top_k,
                                        float score_thr, float nms_thr, float iou_lo, float iou_hi,
                                        int32_t* seed_count, int32_t* seed_index, int32_t* seed_class,
                                        float* seed_score, int32_t* gt_class, float* gt_weight, int32_t* gt_index,
@@ -484,8 +539,8 @@ extern "C" int soswsod_oicr_mine_label(const float* prev, long long ld_prev, con
     int32_t* cand_row = reinterpret_cast<int32_t*>(cand_key + (size_t)K * m0);
     const size_t smem = (size_t)n_pow2 * 8;
     SOSWSOD_CHECK_CUDA(cudaFuncSetAttribute(oicr_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    oicr_topk_kernel<<<dim3(G, K), kOicrThreads, smem, st>>>(prev, ld_prev, gt_classes, G, R, kt, score_thr, n_pow2,
-                                                            cand_key, cand_row);
+    oicr_topk_kernel<<<dim3(G, K), kOicrThreads, smem, st>>>(prev, ld_prev, gt_classes, G, gt_count, R, kt, score_thr,
+                                                            n_pow2, cand_key, cand_row);
     SOSWSOD_CHECK_LAUNCH();
     oicr_nms_label_kernel<<<K, kOicrThreads, 0, st>>>(cand_key, cand_row, boxes, gt_classes, G, R, C, kt, nms_thr,
                                                       iou_lo, iou_hi, seed_count, seed_index, seed_class,

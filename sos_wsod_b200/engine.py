@@ -187,9 +187,12 @@ class OICRPlusHeadEngine:
 
     # -------------------------------------------------------------------------------------------
     def train_step(self, vb: ViewBatch, gt_classes_img: torch.Tensor, dropout_seeds: Tuple[int, int] = (1, 2),
-                   need_feat_grad: bool = True, loss_scale: float = 1.0, grad_hook=None) -> TrainOutput:
+                   need_feat_grad: bool = True, loss_scale: float = 1.0, grad_hook=None,
+                   gt_count: Optional[torch.Tensor] = None, gt_onehot: Optional[torch.Tensor] = None) -> TrainOutput:
         """Forward + backward of the head for one image (V views).  gt_classes_img: int [G] sorted ascending
-        (get_image_level_gt, roi_heads.py:144-164).  Gradients are those of loss_scale * sum(all loss keys).
+        (get_image_level_gt, roi_heads.py:144-164); or, with `gt_count` / `gt_onehot` from ops.image_level_gt, the
+        padded device list [C] whose live length stays on the device (no host synchronisation anywhere in the step).
+        Gradients are those of loss_scale * sum(all loss keys).
         grad_hook(name, [tensors]) is called as soon as the kernels producing a layer's parameter gradients are
         queued -- the data-parallel caller starts that layer's NCCL all-reduce there, so it overlaps the remaining
         backward kernels (the reference gets the same overlap from DDP buckets, tools/train_net_multi.py:75-78)."""
@@ -199,8 +202,12 @@ class OICRPlusHeadEngine:
         C, K, V, R = cfg.num_classes, cfg.refine_k, vb.num_views, vb.R
         dev = vb.obj.device
         gt_int = gt_classes_img.to(device=dev, dtype=torch.int32)
-        gt_oh = torch.zeros((C,), dtype=torch.float32, device=dev)
-        gt_oh[gt_int.long()] = 1.0
+        if gt_count is not None:
+            assert gt_onehot is not None and gt_int.numel() == C
+            gt_oh = gt_onehot
+        else:
+            gt_oh = torch.zeros((C,), dtype=torch.float32, device=dev)
+            gt_oh[gt_int.long()] = 1.0
         boxes = vb.view_boxes()
 
         # ---------------- forward ----------------
@@ -211,7 +218,7 @@ class OICRPlusHeadEngine:
         scores, img_scores, wloss = ops.wsddn_forward(L, 0, C, V, R, C, gt_oh, dlogits=dL)
         prev = ops.oicr_avg_scores(scores, L, cfg.col_ref0, cfg.ref_stride, V, R, C, K)
         mined = ops.oicr_mine_label(prev, boxes[0], gt_int, C, cfg.top_k(R), cfg.mist_thre, cfg.mist_nms,
-                                    cfg.iou_thresholds[0], cfg.iou_thresholds[1])
+                                    cfg.iou_thresholds[0], cfg.iou_thresholds[1], gt_count=gt_count)
         olosses, view_losses, acc = ops.oicr_loss(L, cfg.col_ref0, cfg.ref_stride, boxes, mined["gt_class"],
                                                   mined["gt_weight"], mined["gt_index"], V, R, C, K,
                                                   flip_quirk=cfg.reproduce_flip_quirk and V == 4,

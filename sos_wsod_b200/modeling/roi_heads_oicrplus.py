@@ -42,8 +42,11 @@ class _FusedHeadStep(Function):
     def forward(ctx, engine, vb, gt_int, seeds, n_feats, *tensors):
         feats = tensors[:n_feats]
         need_fg = any(f.requires_grad for f in feats)
+        gt_count = gt_onehot = None
+        if isinstance(gt_int, tuple):      # (padded list, count, one-hot) kept on the device
+            gt_int, gt_count, gt_onehot = gt_int
         out = engine.train_step(ViewBatch([f.detach() for f in feats], vb.rois, vb.obj, vb.R), gt_int, seeds,
-                                need_feat_grad=need_fg, grad_hook=engine.grad_hook)
+                                need_feat_grad=need_fg, grad_hook=engine.grad_hook, gt_count=gt_count, gt_onehot=gt_onehot)
         ctx.engine_out = out
         ctx.deferred = engine.deferred_scale_check
         ctx.n_feats = n_feats
@@ -148,6 +151,10 @@ class OICRPlusHeads(nn.Module):
         # "deferred": assumes sum(loss_dict.values()).backward() and verifies it one step late, without a stall
         self.loss_scale_check = "sync"
         self._deferred = _DeferredScaleCheck()
+        # image-level labels of CUDA targets are derived on the device (soswsod_image_level_gt); False restores the
+        # reference's torch.unique call (identical values, one host synchronisation per step)
+        self.image_level_gt_on_device = True
+        self._gt_dev = None
 
     # ---- construction from config (roi_heads_oicrplus.py:88-147) ----
     @classmethod
@@ -202,6 +209,15 @@ class OICRPlusHeads(nn.Module):
         self._engine.deferred_scale_check = self._deferred if self.loss_scale_check == "deferred" else None
         return self._engine
 
+    def image_level_gt_lists(self):
+        """(gt_classes_img, gt_classes_img_int, gt_classes_img_oh) exactly as get_image_level_gt returns them, for the
+        last forward (reads the class count back when the labels were kept on the device)."""
+        if self._gt_dev is not None:
+            lst, cnt, oh = self._gt_dev
+            g = lst[:int(cnt.item())].to(torch.int64)
+            return [g], [g], oh[None]
+        return self.gt_classes_img, self.gt_classes_img_int, self.gt_classes_img_oh
+
     def check_deferred(self, wait: bool = True) -> None:
         """Raises if a backward run under loss_scale_check='deferred' saw a non-unit upstream gradient."""
         self._deferred.check(wait)
@@ -230,7 +246,18 @@ class OICRPlusHeads(nn.Module):
         features1, features2 = features_list
         proposals1, proposals1_flip, proposals2, proposals2_flip = proposals_list
         targets1 = targets_list[0]
-        self.gt_classes_img, self.gt_classes_img_int, self.gt_classes_img_oh = get_image_level_gt(targets1, self.num_classes)
+        self._gt_dev = None
+        if (self.image_level_gt_on_device and targets1 is not None and len(targets1) == 1
+                and targets1[0].gt_classes.is_cuda and self.num_classes <= 128):
+            # same result as get_image_level_gt, but the number of distinct classes never travels to the host
+            # (torch.unique reads it back, which stalls the host until the previous step has drained)
+            from .. import ops
+            lst, cnt, oh = ops.image_level_gt(targets1[0].gt_classes, self.num_classes)
+            self._gt_dev = (lst, cnt, oh)
+            self.gt_classes_img_oh = oh[None]
+            self.gt_classes_img = self.gt_classes_img_int = None      # materialised on demand: image_level_gt_lists()
+        else:
+            self.gt_classes_img, self.gt_classes_img_int, self.gt_classes_img_oh = get_image_level_gt(targets1, self.num_classes)
         f1 = features1[self.box_in_features[-1]]
         f2 = features2[self.box_in_features[-1]]
         losses = self._forward_box(f1, f2, proposals1, proposals1_flip, proposals2, proposals2_flip)
@@ -246,7 +273,8 @@ class OICRPlusHeads(nn.Module):
         R = len(proposals1[0])
         vb = ViewBatch([features1, features2], rois, obj, R)
         seeds = (torch.initial_seed() * 7919 + 2 * self.iter + 1, torch.initial_seed() * 7919 + 2 * self.iter + 2)
-        outs = _FusedHeadStep.apply(eng, vb, self.gt_classes_img_int[0], seeds, 2, features1, features2, *self._param_list())
+        gt_arg = self._gt_dev if self._gt_dev is not None else self.gt_classes_img_int[0]
+        outs = _FusedHeadStep.apply(eng, vb, gt_arg, seeds, 2, features1, features2, *self._param_list())
         out = eng.last_output
         self.last_metrics = {"acc_counts": out.aux["acc_counts"], "label_counts": out.aux["counts"]}
         return dict(zip(out.losses.keys(), outs))

@@ -291,10 +291,29 @@ def oicr_avg_scores(wsddn_scores: torch.Tensor, logits: Optional[torch.Tensor], 
     return prev
 
 
+def image_level_gt(gt_classes: torch.Tensor, C: int):
+    """get_image_level_gt on the device, without torch.unique's host read-back: gt_classes int64/int32 [n] ->
+    (gt_list int32 [C] ascending distinct classes padded with -1, gt_count int32 [1], gt_onehot fp32 [C])."""
+    _need_cuda(gt_classes)
+    assert gt_classes.dtype in (torch.int64, torch.int32) and gt_classes.dim() == 1
+    gt_classes = gt_classes.contiguous()
+    dev = gt_classes.device
+    lst = torch.empty((C,), dtype=torch.int32, device=dev)
+    cnt = torch.empty((1,), dtype=torch.int32, device=dev)
+    oh = torch.empty((C,), dtype=torch.float32, device=dev)
+    check(_lib.load().soswsod_image_level_gt(_ptr(gt_classes), int(gt_classes.dtype == torch.int64), gt_classes.numel(), C,
+                                             _ptr(lst), _ptr(cnt), _ptr(oh), _stream()), "image_level_gt")
+    _count(1)
+    return lst, cnt, oh
+
+
 def oicr_mine_label(prev: torch.Tensor, boxes: torch.Tensor, gt_classes: torch.Tensor, C: int, top_k: int,
-                    score_thr: float = 0.05, nms_thr: float = 0.01, iou_lo: float = 0.5, iou_hi: float = 0.6):
-    """prev fp32 [K,R,ld]; boxes fp32 [R,4]; gt_classes int32 [G] ascending.  Returns a dict of device tensors."""
-    _need_cuda(prev, boxes, gt_classes)
+                    score_thr: float = 0.05, nms_thr: float = 0.01, iou_lo: float = 0.5, iou_hi: float = 0.6,
+                    gt_count: Optional[torch.Tensor] = None):
+    """prev fp32 [K,R,ld]; boxes fp32 [R,4]; gt_classes int32 [G] ascending (with gt_count, a device int32 scalar, only
+    its first gt_count entries are live and G is the capacity).  Returns a dict of device tensors."""
+    _need_cuda(prev, boxes, gt_classes, gt_count)
+    assert gt_count is None or (gt_count.dtype == torch.int32 and gt_count.numel() == 1)
     assert prev.dtype == torch.float32 and prev.dim() == 3 and prev.is_contiguous()
     K, R, ld = prev.shape
     G = gt_classes.numel()
@@ -315,7 +334,7 @@ def oicr_mine_label(prev: torch.Tensor, boxes: torch.Tensor, gt_classes: torch.T
     lib = _lib.load()
     wsb = lib.soswsod_oicr_mine_workspace_bytes(top_k, G, K)
     ws = torch.empty((wsb,), dtype=torch.uint8, device=dev)
-    check(lib.soswsod_oicr_mine_label(_ptr(prev), ld, _ptr(boxes), _ptr(gt_classes), G, R, C, K, top_k, float(score_thr),
+    check(lib.soswsod_oicr_mine_label(_ptr(prev), ld, _ptr(boxes), _ptr(gt_classes), G, _ptr(gt_count), R, C, K, top_k, float(score_thr),
                                       float(nms_thr), float(iou_lo), float(iou_hi), _ptr(out["seed_count"]),
                                       _ptr(out["seed_index"]), _ptr(out["seed_class"]), _ptr(out["seed_score"]),
                                       _ptr(out["gt_class"]), _ptr(out["gt_weight"]), _ptr(out["gt_index"]),

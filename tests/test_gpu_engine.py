@@ -243,6 +243,17 @@ def test_plugin_surface_train_and_eval(cuda_lib):
             prm.add_(prm.grad, alpha=-1e-3)
     _, losses2 = heads(None, [{"plain5": f1}, {"plain5": f2}], [props(v) for v in views], [targets, None, None, None])
     assert abs(losses2["loss_cls"].item() - losses["loss_cls"].item()) > 0
+    # image-level labels kept on the device (default) == the reference's torch.unique path
+    assert heads._gt_dev is not None
+    ci, cint, coh = heads.image_level_gt_lists()
+    assert cint[0].tolist() == [2, 9] and coh.shape == (1, C) and coh.sum().item() == 2
+    heads.image_level_gt_on_device = False
+    heads.iter -= 1                              # same dropout seeds as the previous call
+    _, losses_host = heads(None, [{"plain5": f1}, {"plain5": f2}], [props(v) for v in views], [targets, None, None, None])
+    assert heads._gt_dev is None and heads.gt_classes_img_int[0].tolist() == [2, 9]
+    for k in losses2:
+        assert losses_host[k].item() == losses2[k].item(), k
+    heads.image_level_gt_on_device = True
     # deferred upstream-gradient check: same gradients without a host stall; a scaled objective is reported late
     g_sync = heads.box_head.fc2.weight.grad.clone()
     heads.loss_scale_check = "deferred"

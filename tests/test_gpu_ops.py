@@ -436,6 +436,35 @@ def test_oicr_mine_label_bit_exact(ops, R, C, G, K, seed):
         assert cnt == [int(((y >= 0) & (y < C)).sum()), int((y == C).sum()), int((y == -1).sum())]
 
 
+def test_image_level_gt_and_device_side_count(ops):
+    """soswsod_image_level_gt == get_image_level_gt (sorted distinct classes, one-hot), and mining with the padded list +
+    device count gives exactly what mining with the host-sized list gives."""
+    g = _gen(91)
+    for C, raw in [(20, [7, 3, 3, 12, 7]), (80, [79, 0, 64, 31, 32, 0]), (20, [5]), (128, list(range(127, -1, -3)))]:
+        gt = torch.tensor(raw, dtype=torch.int64)
+        lst, cnt, oh = ops.image_level_gt(gt.cuda(), C)
+        e_int, e_oh = ref.image_level_gt(gt, C)
+        n = int(cnt.item())
+        assert n == e_int.numel() and torch.equal(lst[:n].cpu().long(), e_int) and bool((lst[n:] == -1).all())
+        assert torch.equal(oh.cpu(), e_oh.reshape(-1))
+        lst32, cnt32, _ = ops.image_level_gt(gt.to(torch.int32).cuda(), C)
+        assert torch.equal(lst32, lst) and torch.equal(cnt32, cnt)
+    R, C, K = 1200, 20, 3
+    prev = torch.stack([ref.synth_prev_scores(R, C + 1, g) for _ in range(K)]).cuda()
+    boxes = ref.synth_boxes(R, 480, 640, g).cuda()
+    gt = torch.tensor([11, 2, 2, 17], dtype=torch.int64).cuda()
+    lst, cnt, _ = ops.image_level_gt(gt, C)
+    a = ops.oicr_mine_label(prev, boxes, torch.unique(gt).to(torch.int32), C, 120)
+    b = ops.oicr_mine_label(prev, boxes, lst, C, 120, gt_count=cnt)
+    for k in range(K):
+        M = int(a["seed_count"][k])
+        assert M == int(b["seed_count"][k])
+        for key in ("seed_index", "seed_class", "seed_score"):
+            assert torch.equal(a[key][k, :M], b[key][k, :M]), key
+    for key in ("gt_class", "gt_weight", "gt_index", "counts"):
+        assert torch.equal(a[key], b[key]), key
+
+
 @pytest.mark.parametrize("R,C,K,quirk", [(2000, 20, 3, True), (500, 80, 2, True), (300, 20, 4, False)])
 def test_oicr_loss_and_grad(ops, R, C, K, quirk):
     g = _gen(200 + R)
