@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define SOSWSOD_ABI_VERSION 5
+#define SOSWSOD_ABI_VERSION 6
 
 #define SOSWSOD_OK 0
 #define SOSWSOD_ERR_INVALID (-1)     /* bad shape / null pointer / misalignment */
@@ -241,6 +241,36 @@ int soswsod_predict(const float* logits, long long ld, int col_ref0, int ref_str
 int soswsod_tta_accumulate(const float* pred_boxes, const float* probs, int R, int C, float scale_x,
                            float scale_y, int flipped, float view_w, int first, float finalize_div,
                            float* acc_boxes, float* acc_probs, soswsod_stream_t stream);
+
+/* Test-time augmentation for ALL views of an image in one launch each.
+ * A view is described by SOSWSOD_TTA_VIEW_PARAMS floats in a HOST array (copied into the launch
+ * parameters, so nothing is read back and the call stays stream-ordered):
+ *   [0] fwd_sx = fp32(new_w * 1.0 / w)   [1] fwd_sy = fp32(new_h * 1.0 / h)      ResizeTransform.apply_coords
+ *   [2] flipped (0 / 1)                  [3] view width new_w   [4] view height new_h
+ *   [5] value written into the roi's batch-index column (index of the view inside its feature tensor)
+ *   [6] inv_sx = fp32(w * 1.0 / new_w)   [7] inv_sy = fp32(h * 1.0 / new_h)      ResizeTransform.inverse()
+ *   [8] post_sx, [9] post_sy: inverse of the reference's pre-transform (:169-173, stored image -> dataset
+ *       size), applied after [6], [7] by soswsod_tta_merge; 1 when the stored image is at the dataset's size
+ *
+ * soswsod_tta_views: the proposal path of DatasetMapperTTAAVG.__call__ / transform_proposals
+ *   (W/modeling/test_time_augmentation_avg.py:29-71, 186-195): TransformList([Resize, HFlip]).apply_box
+ *   (corner min / max after every member), Boxes.clip to the view, Boxes.nonempty(min_box_size)
+ *   (D/structures/boxes.py:183-210).  boxes fp32 [R,4] in original-image coordinates ->
+ *   rois fp32 [V*R, 5] view-major (batch index, x1, y1, x2, y2), keep uint8 [V, R] (the nonempty
+ *   mask), dropped int32 [V] = proposals of the view that fail it (the reference would drop them and
+ *   then fail to average views of different length: the caller treats a non-zero count as an error).
+ *
+ * soswsod_tta_merge: GeneralizedRCNNWithTTAAVG._get_augmented_boxes (:349-371): per view
+ *   tfm.inverse().apply_box (inverse flip about new_w, then * inv_sx / inv_sy), then the mean over views
+ *   (sum in view order, one division by V) of pred_boxes [V, R, 4C] -> [R, 4C] and probs [V, R, C+1] ->
+ *   [R, C+1].  Replaces V device->host->device numpy round trips per image. */
+#define SOSWSOD_TTA_MAX_VIEWS 32
+#define SOSWSOD_TTA_VIEW_PARAMS 10
+int soswsod_tta_views(const float* boxes, int R, const float* view_params_host, int V, float min_box_size,
+                      float* rois, uint8_t* keep, int32_t* dropped, soswsod_stream_t stream);
+int soswsod_tta_merge(const float* pred_boxes, const float* probs, int V, int R, int C,
+                      const float* view_params_host, float* mean_boxes, float* mean_probs,
+                      soswsod_stream_t stream);
 
 /* soswsod_nms: greedy NMS, suppress j when IoU(i,j) > thr (strict); keep = original indices in score-
  * descending order (ties: lower index first).  Replaces torchvision `nms` (D/layers/nms.py:6-7,25);

@@ -525,18 +525,72 @@ def test_forward(view: View, p: HeadParams, num_classes: int, refine_k: int):
     return predict_probs_K(ZK), predict_boxes_K(DK, view.boxes)
 
 
-def tta_inverse_boxes(boxes: torch.Tensor, scale_x: float, scale_y: float, flipped: bool, view_w: int):
-    """W/wsl/modeling/test_time_augmentation_avg.py:353-365 with fvcore TransformList([Resize, HFlip]).inverse():
-    inverse flip first (x' = W_view - x, swapping x1/x2 -- fvcore HFlipTransform.apply_coords then
-    apply_box takes min/max), then inverse resize (x * (w/new_w), y * (h/new_h)).  boxes [n,4]."""
-    b = boxes.clone()
+def resize_shortest_edge(h: int, w: int, size: int, max_size: int) -> Tuple[int, int]:
+    """ResizeShortestEdge.get_transform, U/detectron2/data/transforms/augmentation_impl.py:155-175 -> (new_h, new_w)."""
+    scale = size * 1.0 / min(h, w)
+    if h < w:
+        newh, neww = size, scale * w
+    else:
+        newh, neww = scale * h, size
+    if max(newh, neww) > max_size:
+        scale = max_size * 1.0 / max(newh, neww)
+        newh = newh * scale
+        neww = neww * scale
+    return int(newh + 0.5), int(neww + 0.5)
+
+
+def tta_view_sizes(h: int, w: int, min_sizes: Sequence[int], max_size: int, flip: bool):
+    """DatasetMapperTTAAVG.__call__, W/wsl/modeling/test_time_augmentation_avg.py:175-182: the views in order
+    -> [(new_h, new_w, flipped)]."""
+    out = []
+    for s in min_sizes:
+        nh, nw = resize_shortest_edge(h, w, s, max_size)
+        out.append((nh, nw, False))
+        if flip:
+            out.append((nh, nw, True))
+    return out
+
+
+def _f32(x: float) -> torch.Tensor:
+    return torch.tensor(x, dtype=torch.float64).to(torch.float32)
+
+
+def tta_transform_proposals(boxes: torch.Tensor, hw: Tuple[int, int], new_hw: Tuple[int, int], flipped: bool,
+                            min_box_size: float = 0.0):
+    """transform_proposals, test_time_augmentation_avg.py:29-71 (without the final row filter): TransformList([Resize,
+    HFlip]).apply_box on fp32 numpy boxes (ResizeTransform.apply_coords U/detectron2/data/transforms/transform.py:
+    123-126: x * (new_w * 1.0 / w) with the Python double rounded to fp32 by numpy; fvcore Transform.apply_box takes
+    the min / max of the four transformed corners after every member; HFlipTransform: x -> new_w - x), then
+    Boxes.clip(new_hw) and Boxes.nonempty(min_box_size) (U/detectron2/structures/boxes.py:183-210).
+    -> (boxes [R,4] in view coordinates, keep bool [R])."""
+    (h, w), (nh, nw) = hw, new_hw
+    b = boxes.clone().to(torch.float32)
+    xa, xb = b[:, 0] * _f32(nw * 1.0 / w), b[:, 2] * _f32(nw * 1.0 / w)
+    ya, yb = b[:, 1] * _f32(nh * 1.0 / h), b[:, 3] * _f32(nh * 1.0 / h)
+    x1, x2, y1, y2 = torch.minimum(xa, xb), torch.maximum(xa, xb), torch.minimum(ya, yb), torch.maximum(ya, yb)
     if flipped:
-        x1 = view_w - b[:, 2]
-        x2 = view_w - b[:, 0]
-        b[:, 0], b[:, 2] = x1, x2
-    b[:, 0::2] = b[:, 0::2] * scale_x
-    b[:, 1::2] = b[:, 1::2] * scale_y
-    return b
+        xa, xb = nw - x1, nw - x2
+        x1, x2 = torch.minimum(xa, xb), torch.maximum(xa, xb)
+    out = torch.stack([x1.clamp(min=0, max=nw), y1.clamp(min=0, max=nh), x2.clamp(min=0, max=nw), y2.clamp(min=0, max=nh)], 1)
+    keep = ((out[:, 2] - out[:, 0]) > min_box_size) & ((out[:, 3] - out[:, 1]) > min_box_size)
+    return out, keep
+
+
+def tta_inverse_boxes(boxes: torch.Tensor, scale_x: float, scale_y: float, flipped: bool, view_w: int,
+                      post_scale: Optional[Tuple[float, float]] = None):
+    """W/wsl/modeling/test_time_augmentation_avg.py:353-365 with fvcore TransformList([Resize, HFlip]).inverse():
+    inverse flip first (x' = W_view - x; fvcore HFlipTransform.apply_coords, then apply_box takes the corner
+    min/max), then inverse resize (x * (w/new_w), y * (h/new_h), the Python doubles rounded to fp32), then -- when the
+    mapper composed a pre-transform, :169-173 -- the inverse of that resize (`post_scale`).  boxes [n,4]."""
+    b = boxes.clone()
+    x1, y1, x2, y2 = b[:, 0], b[:, 1], b[:, 2], b[:, 3]
+    if flipped:
+        xa, xb = view_w - x1, view_w - x2
+        x1, x2 = torch.minimum(xa, xb), torch.maximum(xa, xb)
+    for sx, sy in [(scale_x, scale_y)] + ([post_scale] if post_scale is not None else []):
+        xa, xb, ya, yb = x1 * _f32(sx), x2 * _f32(sx), y1 * _f32(sy), y2 * _f32(sy)
+        x1, x2, y1, y2 = torch.minimum(xa, xb), torch.maximum(xa, xb), torch.minimum(ya, yb), torch.maximum(ya, yb)
+    return torch.stack([x1, y1, x2, y2], 1)
 
 
 def tta_merge(all_boxes: Sequence[torch.Tensor], all_scores: Sequence[torch.Tensor]):

@@ -10,7 +10,7 @@ from ctypes import c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_longl
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libsoswsod_b200.so")
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 DTYPE_F32, DTYPE_BF16 = 0, 1
 ARGMAX_I32, ARGMAX_U16 = 0, 1
@@ -47,6 +47,8 @@ SIGNATURES = {
                                  _P, _P]),
     "soswsod_tta_accumulate": (c_int, [_P, _P, c_int, c_int, c_float, c_float, c_int, c_float, c_int, c_float, _P, _P,
                                         _P]),
+    "soswsod_tta_views": (c_int, [_P, c_int, _P, c_int, c_float, _P, _P, _P, _P]),
+    "soswsod_tta_merge": (c_int, [_P, _P, c_int, c_int, c_int, _P, _P, _P, _P]),
     "soswsod_nms_workspace_bytes": (c_size_t, [c_int]),
     "soswsod_nms": (c_int, [_P, _P, c_int, c_float, _P, _P, _P, c_size_t, _P]),
     "soswsod_detect_workspace_bytes": (c_size_t, [c_int, c_int]),

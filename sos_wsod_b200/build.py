@@ -25,6 +25,7 @@ SOURCES = [
     ("wsddn.cu", []),
     ("oicr.cu", ["-fmad=false"]),
     ("nms.cu", ["-fmad=false"]),
+    ("tta.cu", ["-fmad=false"]),
     ("pgf.cu", ["-fmad=false"]),
 ]
 COMMON = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",

@@ -50,6 +50,13 @@ def get_cfg() -> CfgNode:
     cfg.WSL = C(REFINE_NUM=3, REFINE_REG=[True, True, True, True], REFINE_MIST=True, MIST_P=0.10, MIST_THRE=0.05,
                 MIST_TYPE="nms", MEAN_LOSS=True)
     cfg.OICRPLUS = C(BBOX_UPDATE=False, PROPOSAL_NUM=2000)
-    cfg.TEST = C(DETECTIONS_PER_IMAGE=100)
+    # detection_result_test.yaml:46-50 (shipped with ENABLED: False), Base-RCNN-DilatedC5.yaml:4-10
+    cfg.TEST = C(DETECTIONS_PER_IMAGE=100, AUG=C(ENABLED=False, MIN_SIZES=(480, 576, 672, 768, 864, 960, 1056, 1152),
+                                                  MAX_SIZE=4000, FLIP=True))
+    cfg.INPUT = C(FORMAT="BGR")
+    cfg.DATASETS = C(PRECOMPUTED_PROPOSAL_TOPK_TRAIN=4000, PRECOMPUTED_PROPOSAL_TOPK_TEST=4000)
+    cfg.MODEL.LOAD_PROPOSALS = True
+    cfg.MODEL.MASK_ON = False
+    cfg.MODEL.KEYPOINT_ON = False
     cfg.SOLVER = C(AMP=C(ENABLED=False))
     return cfg

@@ -11,6 +11,8 @@
 //                          row-major order (first maximum wins), empty bin -> (0, -1), the stored value is the
 //                          cell's own bit pattern.
 //   roi_pool_bwd_fast      see the comment above the kernel.
+#include <stdlib.h>
+
 #include "roi_plan.cuh"
 #include "tma.cuh"
 
@@ -754,6 +756,428 @@ static int launch_bwd_fast_t(const void* grad, long long ld_grad, const uint16_t
     return 1;
 }
 
+// ------------------------------------------------------------------------------------------------
+// backward, queued (v8): the read-add-write chain of a plane pair is the critical path of this kernel (the steps of
+// one roi and of consecutive rois may touch the same cell, so they run in order), and every cycle a chain spends on
+// anything else -- preparing operands, probing an mbarrier (90-150 cycles per probe), handing a token to the next
+// warp -- is lost.  Here each plane pair has ONE accumulator warp that does nothing but the chain, fed through a
+// shared-memory queue by P preparation warps:
+//
+//   TMA warp      as above: streams [RT rois x BW columns] tiles of arg-max / grad_out through the mbarrier ring.
+//   prep warps    P per plane pair, rois dealt round-robin.  A prep warp turns its roi into up to 4 colour steps of
+//                 32 (shared address, scaled gradient) pairs and stores them as 64-bit entries into its queue slot;
+//                 rois with more than 4 colour steps (narrower than 7 cells) send further chunks through the same slot.
+//   accumulator   per roi: loads its slot's 4 x 32 entries (prefetched while the previous roi accumulates), checks
+//                 the tag every entry carries, releases the slot, runs the 4 ordered read-add-write steps.
+//
+// Queue protocol without fences or mbarriers on the accumulator's path: an entry is ONE 64-bit shared store
+// {address (18 bits) | more << 18 | tag << 19, value}; the tag names the slot's use (round, chunk), so an entry whose
+// tag matches is complete and current.  The slot goes back to its prep warp through a plain token word the
+// accumulator writes after the entries are in its registers (single writer, single reader).
+// Result: deterministic (fixed order per plane), atomic-free, bit-identical to the turn-token kernel above.
+constexpr int kBwdQSteps = 4;                       // colour steps per queue slot
+constexpr int kBwdQSlotBytes = kBwdQSteps * 32 * 8;
+constexpr int kBwdQMaxP = 4;
+
+struct BwdQCfg {
+    BwdFastCfg b;
+    int P, D;          // prep warps per plane pair, slots per prep warp (queue depth Q = P * D)
+};
+
+__device__ __forceinline__ void q_load(uint32_t qa, uint32_t (&lo)[kBwdQSteps], uint32_t (&hi)[kBwdQSteps]) {
+#pragma unroll
+    for (int k = 0; k < kBwdQSteps; ++k)
+        asm volatile("ld.volatile.shared.v2.u32 {%0, %1}, [%2];" : "=r"(lo[k]), "=r"(hi[k]) : "r"(qa + 256u * k) : "memory");
+}
+
+template <typename GradT>
+__global__ void __launch_bounds__((kBwdFastMaxCT / 2 * (1 + kBwdQMaxP) + 1) * 32, 1)
+roi_pool_bwd_q_kernel(const __grid_constant__ CUtensorMap tmap_arg, const __grid_constant__ CUtensorMap tmap_grad,
+                      const int* __restrict__ img_start, const int* __restrict__ order,
+                      const RoiRecord* __restrict__ rec, int C, int H, int W, float* __restrict__ grad_feat, BwdQCfg qc) {
+    constexpr int PP = kPP;
+    extern __shared__ uint8_t smem_raw[];
+    const BwdFastCfg& cfg = qc.b;
+    const int CT = cfg.CT, BW = cfg.BW, nbox = cfg.nbox, S = cfg.stages, RT = cfg.RT;
+    const int P = qc.P, D = qc.D, Q = P * D;
+    const int NP = (CT + 1) >> 1;   // plane pairs = accumulator warps
+    const int NPREP = NP * P;
+    const uint32_t base = (smem_u32(smem_raw) + 127u) & ~127u;
+    uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
+    float* planes = reinterpret_cast<float*>(gen_base);                          // [CT][plane_stride]
+    const uint32_t plane_bytes = (uint32_t)CT * cfg.plane_stride * 4;            // multiple of 128
+    const uint32_t arg_box = (uint32_t)RT * BW * 2;
+    const uint32_t grad_box = (uint32_t)RT * BW * sizeof(GradT);
+    const uint32_t arg_stage = nbox * arg_box, grad_stage = nbox * grad_box;
+    const uint32_t ring_off = plane_bytes;
+    const uint32_t queue_off = ring_off + S * (arg_stage + grad_stage);          // [NP][Q][4][32] x 8 bytes
+    const uint32_t bar_off = queue_off + (uint32_t)NP * Q * kBwdQSlotBytes;
+    auto full_bar = [&](int st) { return base + bar_off + 8u * st; };
+    auto empty_bar = [&](int st) { return base + bar_off + 8u * (S + st); };
+    const uint32_t token_off = bar_off + 16u * S;                                // [NP][Q] uint32 slot tokens
+    const uint32_t meta_off = token_off + 4u * (kBwdFastMaxCT / 2) * (kBwdQMaxP * 2);
+    BwdMeta* s_meta = reinterpret_cast<BwdMeta*>(gen_base + meta_off);           // [S][kBwdFastMaxRT]
+    float* s_dummy = reinterpret_cast<float*>(s_meta + S * kBwdFastMaxRT);        // [32] idle-lane targets
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int groups = (C + CT - 1) / CT;
+    int bid = blockIdx.x;
+    const int band = bid % cfg.bands;
+    bid /= cfg.bands;
+    const int c0 = (bid % groups) * CT;
+    const int b = bid / groups;
+    const int HW = H * W;
+    const int band_lo = min(band * cfg.band_rows, H) * W;
+    const int band_hi = min((band + 1) * cfg.band_rows, H) * W;
+
+    for (int i = threadIdx.x; i < CT * cfg.plane_stride; i += blockDim.x) planes[i] = 0.f;
+    {
+        uint32_t* z = reinterpret_cast<uint32_t*>(gen_base + queue_off);
+        const int nz = (int)((meta_off - queue_off) / 4);      // queue entries (tag 0 = invalid), barriers, tokens
+        for (int i = threadIdx.x; i < nz; i += blockDim.x) z[i] = 0u;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int st = 0; st < S; ++st) {
+            mbar_init(full_bar(st), 1);
+            mbar_init(empty_bar(st), NPREP);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const int seg_lo = img_start[b], seg_hi = img_start[b + 1];
+    const int r_lo = seg_hi > seg_lo ? __ldg(order + seg_lo) : 0;
+    const int r_hi = seg_hi > seg_lo ? __ldg(order + seg_hi - 1) + 1 : 0;
+    const int nrois = r_hi - r_lo;
+    const int ntiles = (nrois + RT - 1) / RT;
+    const int total_cols = C * PP;
+    const int col0 = c0 * PP;
+    const int col_a = col0 & ~7;
+    const int col_g = col0 & ~(16 / (int)sizeof(GradT) - 1);
+
+    if (warp == NP + NPREP) {
+        // ---- TMA warp ----
+        uint32_t tx = 0;
+        for (int bx = 0; bx < nbox; ++bx) {
+            if (col_a + bx * BW < total_cols) tx += arg_box;
+            if (col_g + bx * BW < total_cols) tx += grad_box;
+        }
+        int st = 0;
+        uint32_t phase = 0;
+        for (int t = 0; t < ntiles; ++t) {
+            const int r0 = r_lo + t * RT;
+            BwdMeta meta;
+            meta.scale = 0.f;
+            meta.code = 0;
+            if (lane < RT && r0 + lane < r_hi) {
+                const uint2 tail = __ldg(reinterpret_cast<const uint2*>(rec + r0 + lane) + 7);   // bytes 56..63
+                if ((int)(tail.x >> 16) == b) {
+                    meta.scale = __uint_as_float(tail.y);
+                    meta.code = 1 | ((tail.x & 0xFFu) << 8) | (((tail.x >> 8) & 0xFFu) << 16);
+                }
+            }
+            mbar_wait(empty_bar(st), phase ^ 1u);
+            if (lane < RT) s_meta[st * kBwdFastMaxRT + lane] = meta;
+            __syncwarp();
+            if (lane == 0) {
+                mbar_expect_tx(full_bar(st), tx);
+                const uint32_t sa = base + ring_off + st * (arg_stage + grad_stage);
+                const uint32_t sg = sa + arg_stage;
+                for (int bx = 0; bx < nbox; ++bx) {
+                    if (col_a + bx * BW < total_cols) tma_load_2d(sa + bx * arg_box, &tmap_arg, full_bar(st), col_a + bx * BW, r0);
+                    if (col_g + bx * BW < total_cols) tma_load_2d(sg + bx * grad_box, &tmap_grad, full_bar(st), col_g + bx * BW, r0);
+                }
+            }
+            if (++st == S) {
+                st = 0;
+                phase ^= 1u;
+            }
+        }
+    } else if (warp < NP) {
+        // ---- accumulator warp of plane pair `warp` ----
+        const int pair = warp;
+        const uint32_t qbase = base + queue_off + (uint32_t)pair * Q * kBwdQSlotBytes + 8u * lane;
+        const uint32_t tok_s = base + token_off + 4u * (pair * Q);
+        uint32_t lo[kBwdQSteps], hi[kBwdQSteps], nlo[kBwdQSteps], nhi[kBwdQSteps];
+        int s = 0, round = 0;
+        if (nrois > 0) q_load(qbase, lo, hi);
+        for (int r = 0; r < nrois; ++r) {
+            const uint32_t qa = qbase + (uint32_t)s * kBwdQSlotBytes;
+            int ns = s + 1, nround = round;
+            if (ns == Q) {
+                ns = 0;
+                ++nround;
+            }
+            int k = 0;
+            while (true) {
+                const uint32_t tag = 0x1000u | (((uint32_t)round & 0xFFu) << 4) | (uint32_t)k;
+                while (true) {
+                    bool ok = true;
+#pragma unroll
+                    for (int i = 0; i < kBwdQSteps; ++i) ok = ok && (lo[i] >> 19) == tag;
+                    if (__all_sync(FULL_MASK, ok)) break;
+                    q_load(qa, lo, hi);
+                }
+                const bool more = (lo[0] >> 18) & 1u;
+                // the entries are in registers: hand the slot back, then start fetching the next roi's slot
+                if (lane == 0)
+                    asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(tok_s + 4u * s), "r"((((uint32_t)r << 4) | (uint32_t)k) + 1u) : "memory");
+                if (!more && r + 1 < nrois) q_load(qbase + (uint32_t)ns * kBwdQSlotBytes, nlo, nhi);
+#pragma unroll
+                for (int i = 0; i < kBwdQSteps; ++i) {
+                    const uint32_t ad = lo[i] & 0x3FFFFu;
+                    float v;
+                    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(ad) : "memory");
+                    v += __uint_as_float(hi[i]);
+                    asm volatile("st.shared.f32 [%0], %1;" ::"r"(ad), "f"(v) : "memory");
+                    __syncwarp();   // colour classes of one roi may share cells: order the steps
+                }
+                if (!more) break;
+                ++k;
+                q_load(qa, lo, hi);
+            }
+#pragma unroll
+            for (int i = 0; i < kBwdQSteps; ++i) {
+                lo[i] = nlo[i];
+                hi[i] = nhi[i];
+            }
+            s = ns;
+            round = nround;
+        }
+    } else {
+        // ---- preparation warp j of plane pair `pair` ----
+        const int pw_ = warp - NP;
+        const int pair = pw_ / P, j = pw_ - pair * P;
+        const int half = lane >> 4, la = (lane >> 2) & 3, lb = lane & 3;
+        const int chan = 2 * pair + half;
+        const bool chan_ok = chan < CT && (c0 + chan) < C;
+        const uint32_t my_s = smem_u32(planes + (chan_ok ? chan : 0) * cfg.plane_stride);
+        const uint32_t dummy_s = smem_u32(s_dummy) + 4u * lane;
+        const int ea0 = chan * PP + (col0 - col_a);
+        const int eg0 = chan * PP + (col0 - col_g);
+        const unsigned band_cells = (unsigned)(band_hi - band_lo);
+        const int wrap = (RT - 1) * BW;
+        const uint32_t ring_s = base + ring_off;
+        const uint32_t stage_bytes = arg_stage + grad_stage;
+        const uint32_t qpair = base + queue_off + (uint32_t)pair * Q * kBwdQSlotBytes + 8u * lane;
+        const uint32_t tok_s = base + token_off + 4u * (pair * Q);
+        constexpr int kCode22 = 1 | (2 << 8) | (2 << 16);
+        int e22a[4], e22g[4];
+        bool v22[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int ph = 2 * la + (k >> 1), pw = 2 * lb + (k & 1);
+            v22[k] = chan_ok && ph < kPlanP && pw < kPlanP;
+            int e = ea0 + ph * kPlanP + pw;
+            e22a[k] = e + (e >= BW ? wrap : 0);
+            e = eg0 + ph * kPlanP + pw;
+            e22g[k] = e + (e >= BW ? wrap : 0);
+        }
+        uint32_t last_tok[2] = {0u, 0u};   // last token written per own slot (D <= 2)
+        int d = 0;                          // own slot counter: slot = j + d * P
+        int round = 0;                      // r / Q of the current roi
+        int st = 0;
+        uint32_t phase = 0;
+        int r = j;
+        for (int t = 0; t < ntiles; ++t) {
+            const int tile_end = min((t + 1) * RT, nrois);
+            // every prep warp waits for every tile, also one that holds none of its rois: its arrival on the empty
+            // barrier must not run ahead into the stage's previous phase
+            mbar_wait(full_bar(st), phase);
+            const uint32_t sa = ring_s + st * stage_bytes;
+            const uint32_t sg = sa + arg_stage;
+            const BwdMeta* metas = s_meta + st * kBwdFastMaxRT;
+            for (; r < tile_end; r += P) {
+                const int rr = r - t * RT;
+                const BwdMeta m = metas[rr];
+                const int mh = (m.code >> 8) & 0xFF, mw = (m.code >> 16) & 0xFF;
+                const int nsteps = mh * mw;                     // 0 for a roi of another image
+                const int rowe = rr * BW;
+                const int slot = j + d * P;
+                const uint32_t qa = qpair + (uint32_t)slot * kBwdQSlotBytes;
+                const uint32_t tka = tok_s + 4u * slot;
+                auto operand = [&](int ea, int eg, uint32_t& ad, uint32_t& vl) {
+                    unsigned a, graw;
+                    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(a) : "r"(sa + 2u * (unsigned)(ea + rowe)));
+                    if (sizeof(GradT) == 2) {
+                        asm volatile("ld.shared.u16 %0, [%1];" : "=r"(graw) : "r"(sg + 2u * (unsigned)(eg + rowe)));
+                        graw <<= 16;
+                    } else {
+                        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(graw) : "r"(sg + 4u * (unsigned)(eg + rowe)));
+                    }
+                    const unsigned rel = a - (unsigned)band_lo;   // empty bin (0xFFFF) and other bands fail the test
+                    const bool ok = rel < band_cells;
+                    ad = ok ? my_s + 4u * rel : dummy_s;
+                    vl = ok ? __float_as_uint(__uint_as_float(graw) * m.scale) : 0u;
+                };
+                auto publish = [&](const uint32_t (&ad)[kBwdQSteps], const uint32_t (&vl)[kBwdQSteps], int k, bool more) {
+                    const uint32_t want = d ? last_tok[1] : last_tok[0];
+                    uint32_t seen;
+                    do {
+                        asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(seen) : "r"(tka) : "memory");
+                    } while (seen != want);
+                    const uint32_t hdr = ((0x1000u | (((uint32_t)round & 0xFFu) << 4) | (uint32_t)k) << 19) | (more ? (1u << 18) : 0u);
+#pragma unroll
+                    for (int i = 0; i < kBwdQSteps; ++i)
+                        asm volatile("st.volatile.shared.v2.u32 [%0], {%1, %2};" ::"r"(qa + 256u * i), "r"(ad[i] | hdr), "r"(vl[i]) : "memory");
+                    const uint32_t tok = (((uint32_t)r << 4) | (uint32_t)k) + 1u;
+                    if (d) last_tok[1] = tok; else last_tok[0] = tok;
+                };
+                uint32_t ad[kBwdQSteps], vl[kBwdQSteps];
+                if (m.code == kCode22) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        ad[k] = dummy_s;
+                        vl[k] = 0u;
+                        if (v22[k]) operand(e22a[k], e22g[k], ad[k], vl[k]);
+                    }
+                    publish(ad, vl, 0, false);
+                } else if (nsteps > 0) {
+                    const int bin0 = la * mh * kPlanP + lb * mw;
+                    const int ih = chan_ok ? min(mh, kPlanP - la * mh) : 0;   // <= 0: block outside the grid
+                    const int jw = min(mw, kPlanP - lb * mw);
+                    int i = 0, jj = 0, kchunk = 0;
+                    for (int s0 = 0; s0 < nsteps; s0 += kBwdQSteps, ++kchunk) {
+                        const int n = min(kBwdQSteps, nsteps - s0);
+#pragma unroll
+                        for (int k = 0; k < kBwdQSteps; ++k) {
+                            ad[k] = dummy_s;
+                            vl[k] = 0u;
+                            if (k < n) {
+                                if (i < ih && jj < jw) {
+                                    const int bin = bin0 + i * kPlanP + jj;
+                                    int ea = ea0 + bin, eg = eg0 + bin;
+                                    ea += (ea >= BW ? wrap : 0);
+                                    eg += (eg >= BW ? wrap : 0);
+                                    operand(ea, eg, ad[k], vl[k]);
+                                }
+                                if (++jj == mw) {
+                                    jj = 0;
+                                    ++i;
+                                }
+                            }
+                        }
+                        publish(ad, vl, kchunk, s0 + kBwdQSteps < nsteps);
+                    }
+                } else {
+#pragma unroll
+                    for (int k = 0; k < kBwdQSteps; ++k) {
+                        ad[k] = dummy_s;
+                        vl[k] = 0u;
+                    }
+                    publish(ad, vl, 0, false);
+                }
+                if (++d == D) {
+                    d = 0;
+                    ++round;
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty_bar(st));
+            if (++st == S) {
+                st = 0;
+                phase ^= 1u;
+            }
+        }
+    }
+    __syncthreads();
+    const int band_cells = band_hi - band_lo;
+    for (int c = 0; c < CT && c0 + c < C; ++c) {
+        float* dst = grad_feat + ((size_t)b * C + c0 + c) * HW + band_lo;
+        const float* src = planes + c * cfg.plane_stride;
+        for (int i = threadIdx.x; i < band_cells; i += blockDim.x) dst[i] = src[i];
+    }
+}
+
+static bool pick_bwd_q_cfg(int n, int c, int h, int w, int grad_bytes, BwdQCfg* out) {
+    const int max_smem = device_max_smem();
+    const int sms = device_num_sms();
+    const int align_elems = 16 / (2 < grad_bytes ? 2 : grad_bytes);
+    bool found = false;
+    double best_cost = 0;
+    for (int bands = 1; bands <= 64; ++bands) {
+        const int band_rows = (h + bands - 1) / bands;
+        if (bands > 1 && (long long)(bands - 1) * band_rows >= h) continue;  // empty last band
+        const int plane_stride = ((band_rows * w + 31) / 32) * 32;
+        for (int CT = kBwdFastMaxCT; CT >= 1; --CT) {
+            if (CT > c) continue;
+            const int NP = (CT + 1) / 2;
+            const int cols = CT * kPP + align_elems - 1;
+            const int nbox = (cols + 247) / 248;
+            const int BW = (((cols + nbox - 1) / nbox) + 7) / 8 * 8;
+            if (BW > 256 || nbox > 2) continue;
+            for (int P = kBwdQMaxP; P >= 2; --P)
+                for (int D = 2; D >= 1; --D) {
+                    const size_t fixed = (size_t)CT * plane_stride * 4 + (size_t)NP * P * D * kBwdQSlotBytes + 128 /*align*/ +
+                                         1792 /*barriers, tokens, roi meta, dummies*/;
+                    for (int RT = kBwdFastMaxRT; RT >= 8; RT >>= 1) {   // RT * BW * 2 bytes per box: a multiple of 128
+                        const size_t stage = (size_t)nbox * RT * BW * (2 + grad_bytes);
+                        if (fixed + 2 * stage > (size_t)max_smem) continue;
+                        int stages = (int)(((size_t)max_smem - fixed) / stage);
+                        if (stages > 6) stages = 6;
+                        const long long ctas = (long long)n * ((c + CT - 1) / CT) * bands;
+                        const long long waves = (ctas + sms - 1) / sms;
+                        // time ~ waves (every CTA streams all rois of its image; its chains advance together); then
+                        // prefer enough prep warps and queue depth to keep the accumulators fed, then a deeper ring
+                        const double cost = (double)waves + 0.02 * (kBwdQMaxP - P) + (D < 2 ? 0.01 : 0.0) +
+                                            (stages < 3 ? 0.005 : 0.0) + ((CT & 1) ? 0.01 : 0.0);
+                        if (!found || cost < best_cost - 1e-9) {
+                            found = true;
+                            best_cost = cost;
+                            out->b.CT = CT;
+                            out->b.bands = bands;
+                            out->b.band_rows = band_rows;
+                            out->b.nbox = nbox;
+                            out->b.BW = BW;
+                            out->b.stages = stages;
+                            out->b.RT = RT;
+                            out->b.plane_stride = plane_stride;
+                            out->b.smem = fixed + (size_t)stages * stage;
+                            out->P = P;
+                            out->D = D;
+                        }
+                        if (stages >= 3) break;
+                    }
+                }
+        }
+        if (found && best_cost < 1.5) break;
+    }
+    return found;
+}
+
+template <typename GradT>
+static int launch_bwd_q_t(const void* grad, long long ld_grad, const uint16_t* argmax, int R, const void* plan, int n, int c,
+                          int h, int w, float* grad_feat, cudaStream_t st) {
+    BwdQCfg qc;
+    if (!pick_bwd_q_cfg(n, c, h, w, (int)sizeof(GradT), &qc)) return 0;
+    const BwdFastCfg& cfg = qc.b;
+    CUtensorMap ta, tg;
+    int rc = make_tmap_2d(&ta, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, argmax, R, (long long)c * kPP, (long long)c * kPP, cfg.BW,
+                          cfg.RT, CU_TENSOR_MAP_SWIZZLE_NONE);
+    if (rc) return rc;
+    rc = make_tmap_2d(&tg, sizeof(GradT) == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
+                      (int)sizeof(GradT), grad, R, (long long)c * kPP, ld_grad, cfg.BW, cfg.RT, CU_TENSOR_MAP_SWIZZLE_NONE);
+    if (rc) return rc;
+    const PlanView pv = plan_view(plan, R);
+    const int grid = n * ((c + cfg.CT - 1) / cfg.CT) * cfg.bands;
+    const int threads = ((cfg.CT + 1) / 2 * (1 + qc.P) + 1) * 32;
+    auto kern = roi_pool_bwd_q_kernel<GradT>;
+    SOSWSOD_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem));
+    kern<<<grid, threads, cfg.smem, st>>>(ta, tg, pv.img_start, pv.order, pv.rec, c, h, w, grad_feat, qc);
+    SOSWSOD_CHECK_LAUNCH();
+    return 1;
+}
+
+// SOSWSOD_ROI_BWD=turn selects the turn-token kernel (v7) instead of the queued one (v8); read once.
+static bool bwd_use_queue() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("SOSWSOD_ROI_BWD");
+        v = (e && e[0] == 't') ? 0 : 1;
+    }
+    return v == 1;
+}
+
 int launch_bwd_fast(const void* grad, int grad_dtype, long long ld_grad, const uint16_t* argmax, int R, const void* plan,
                     int n, int c, int h, int w, float* grad_feat, cudaStream_t st) {
     if (n > kPlanMaxImages) return 0;
@@ -761,6 +1185,12 @@ int launch_bwd_fast(const void* grad, int grad_dtype, long long ld_grad, const u
     const bool aligned = ((uintptr_t)grad & 15) == 0 && ((uintptr_t)argmax & 15) == 0 && ((ld_grad * gb) & 15) == 0 &&
                          (((long long)c * kPP * 2) & 15) == 0;
     if (!aligned) return 0;
+    if (bwd_use_queue()) {
+        const int rc = grad_dtype == SOSWSOD_DTYPE_BF16
+                           ? launch_bwd_q_t<__nv_bfloat16>(grad, ld_grad, argmax, R, plan, n, c, h, w, grad_feat, st)
+                           : launch_bwd_q_t<float>(grad, ld_grad, argmax, R, plan, n, c, h, w, grad_feat, st);
+        if (rc != 0) return rc;   // 0: no queued configuration fits; fall through to the turn-token kernel
+    }
     if (grad_dtype == SOSWSOD_DTYPE_BF16)
         return launch_bwd_fast_t<__nv_bfloat16>(grad, ld_grad, argmax, R, plan, n, c, h, w, grad_feat, st);
     return launch_bwd_fast_t<float>(grad, ld_grad, argmax, R, plan, n, c, h, w, grad_feat, st);

@@ -88,7 +88,7 @@ class OICROutputLayers(nn.Module):
 
     def inference(self, predictions_K, proposals: List[Instances]):
         """predict_probs_K / predict_boxes_K + fast_rcnn_inference for ONE image -> ([Instances], [row indices],
-        all_scores [1,R,C+1], all_boxes [1,R,4C])."""
+        all_scores [[1,R,C+1]], all_boxes [[1,R,4C]]) -- per-image lists like fast_rcnn_oicr.py:46-83."""
         C = self.num_classes
         if isinstance(predictions_K[0], tuple):
             preds = list(predictions_K)
@@ -100,7 +100,7 @@ class OICROutputLayers(nn.Module):
         probs, pboxes = ops.predict(L, 0, 5 * C + 1, p.proposal_boxes.tensor, C, K, self.bbox_reg_weights)
         return _detections_to_instances(ops.detect(probs, pboxes, p.image_size, self.test_score_thresh,
                                                    self.test_nms_thresh, self.test_topk_per_image),
-                                        p.image_size) + (probs.unsqueeze(0), pboxes.unsqueeze(0))
+                                        p.image_size) + ([probs.unsqueeze(0)], [pboxes.unsqueeze(0)])
 
 
 def _detections_to_instances(det, image_size):

@@ -280,7 +280,8 @@ class OICRPlusHeads(nn.Module):
         return dict(zip(out.losses.keys(), outs))
 
     def _forward_box_test(self, features, proposals, targets=None):
-        """roi_heads_oicrplus.py:432-475: single view -> ([Instances], all_scores [1,R,C+1], all_boxes [1,R,4C])."""
+        """roi_heads_oicrplus.py:432-475: single view -> ([Instances], all_scores, all_boxes) with, as in the reference
+        (fast_rcnn_oicr.py:46-83 returns per-image lists), all_scores = [[1,R,C+1]] and all_boxes = [[1,R,4C]]."""
         eng = self.engine()
         if isinstance(features, dict):
             f = features[self.box_in_features[-1]]
@@ -293,7 +294,7 @@ class OICRPlusHeads(nn.Module):
         vb = ViewBatch([f], rois, obj, len(proposals[0]))
         probs, pboxes = eng.test_forward(vb)
         inst, _ = _detections_to_instances(eng.detect(probs[0], pboxes[0], proposals[0].image_size), proposals[0].image_size)
-        return inst, probs, pboxes
+        return inst, [probs], [pboxes]
 
 
 def build_roi_heads(cfg, input_shape):

@@ -389,6 +389,58 @@ def tta_accumulate(pred_boxes: torch.Tensor, probs: torch.Tensor, scale_x: float
     _count(1)
 
 
+TTA_VIEW_PARAMS = 10   # SOSWSOD_TTA_VIEW_PARAMS
+
+
+def _view_params_host(view_params) -> "ctypes.Array":
+    import ctypes
+
+    flat = [float(x) for row in view_params for x in row]
+    if len(flat) % TTA_VIEW_PARAMS != 0:
+        raise RuntimeError("view_params: 10 floats per view (include/soswsod_b200.h, SOSWSOD_TTA_VIEW_PARAMS)")
+    return (ctypes.c_float * len(flat))(*flat), len(flat) // TTA_VIEW_PARAMS
+
+
+def tta_views(boxes: torch.Tensor, view_params, min_box_size: float = 0.0):
+    """DatasetMapperTTAAVG's proposal path for all V views of an image in one launch.  boxes fp32 [R,4] in
+    original-image coordinates; view_params: V rows of 10 floats (see the header).  Returns (rois [V*R,5] view-major,
+    keep bool [V,R], dropped int32 [V]) -- device tensors, no host synchronisation."""
+    _need_cuda(boxes)
+    import ctypes
+
+    boxes = boxes.contiguous().float()
+    R = boxes.size(0)
+    arr, V = _view_params_host(view_params)
+    rois = torch.empty((V * R, 5), dtype=torch.float32, device=boxes.device)
+    keep = torch.empty((V, R), dtype=torch.uint8, device=boxes.device)
+    dropped = torch.empty((V,), dtype=torch.int32, device=boxes.device)
+    check(_lib.load().soswsod_tta_views(_ptr(boxes), R, ctypes.cast(arr, ctypes.c_void_p), V, float(min_box_size),
+                                        _ptr(rois), _ptr(keep), _ptr(dropped), _stream()), "tta_views")
+    _count(1)
+    return rois, keep.bool(), dropped
+
+
+def tta_merge(pred_boxes: torch.Tensor, probs: torch.Tensor, view_params):
+    """GeneralizedRCNNWithTTAAVG._get_augmented_boxes for all views in one launch: pred_boxes [V,R,4C] and probs
+    [V,R,C+1] in each view's coordinates -> (mean boxes [R,4C] in original-image coordinates, mean probs [R,C+1])."""
+    _need_cuda(pred_boxes, probs)
+    import ctypes
+
+    V, R, C1 = probs.shape
+    C = C1 - 1
+    arr, nv = _view_params_host(view_params)
+    if nv != V or tuple(pred_boxes.shape) != (V, R, 4 * C):
+        raise RuntimeError(f"tta_merge: {nv} view rows / boxes {tuple(pred_boxes.shape)} for probs {tuple(probs.shape)}")
+    pred_boxes = pred_boxes.contiguous()
+    probs = probs.contiguous()
+    mb = torch.empty((R, 4 * C), dtype=torch.float32, device=probs.device)
+    mp = torch.empty((R, C1), dtype=torch.float32, device=probs.device)
+    check(_lib.load().soswsod_tta_merge(_ptr(pred_boxes), _ptr(probs), V, R, C, ctypes.cast(arr, ctypes.c_void_p), _ptr(mb),
+                                        _ptr(mp), _stream()), "tta_merge")
+    _count(1)
+    return mb, mp
+
+
 def nms(boxes: torch.Tensor, scores: torch.Tensor, iou_thr: float) -> torch.Tensor:
     """torchvision.ops.nms drop-in: int64 indices of kept boxes, score-descending.  (One D2H read of the count.)"""
     _need_cuda(boxes, scores)

@@ -274,7 +274,9 @@ def test_plugin_surface_train_and_eval(cuda_lib):
     # eval
     heads.eval()
     inst, empty, all_scores, all_boxes = heads(None, {"plain5": f1[:1].detach()}, props(views[0]), None)
-    assert empty == {} and all_scores.shape == (1, R, C + 1) and all_boxes.shape == (1, R, 4 * C)
+    # per-image lists of [1, R, .] tensors, the structure the reference's TTA wrapper iterates (fast_rcnn_oicr.py:46-83)
+    assert empty == {} and len(all_scores) == 1 and len(all_boxes) == 1
+    assert all_scores[0].shape == (1, R, C + 1) and all_boxes[0].shape == (1, R, 4 * C)
     assert len(inst) == 1 and len(inst[0].scores) <= cfg.TEST.DETECTIONS_PER_IMAGE
     assert (inst[0].scores[:-1] >= inst[0].scores[1:]).all()
 

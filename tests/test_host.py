@@ -168,3 +168,35 @@ def test_data_parallel_gradient_hook_gloo_world2(tmp_path):
     outs = [p.communicate(timeout=120)[0] for p in procs]
     for p, o in zip(procs, outs):
         assert p.returncode == 0, o
+
+
+def test_tta_mapper_host_side_matches_reference_views():
+    """DatasetMapperTTAAVG mirror: view order / sizes (ResizeShortestEdge arithmetic) and the PIL-resized, flipped
+    pixels equal what the reference's own mapper produced (tests/golden/tta_golden.pt); the launch parameters carry
+    the reference's Python-double scale factors."""
+    import hashlib
+
+    from sos_wsod_b200.config import get_cfg
+    from sos_wsod_b200.modeling.test_time_augmentation_avg import DatasetMapperTTAAVG, ViewSpec, resize_shortest_edge
+
+    gold = torch.load(os.path.join(ROOT, "tests", "golden", "tta_golden.pt"), weights_only=False)
+    for c in gold["cases"]:
+        cfg = get_cfg()
+        cfg.MODEL.DEVICE = "cpu"
+        cfg.TEST.AUG.MIN_SIZES, cfg.TEST.AUG.MAX_SIZE, cfg.TEST.AUG.FLIP = c["min_sizes"], c["max_size"], c["flip"]
+        cfg.DATASETS.PRECOMPUTED_PROPOSAL_TOPK_TEST = c["topk"]
+        mapper = DatasetMapperTTAAVG(cfg)
+        h, w = c["stored_hw"]
+        specs = mapper.view_specs(h, w)
+        assert len(specs) == len(c["views"])
+        img = c["image"].permute(1, 2, 0).numpy()
+        for s, v in zip(specs, c["views"]):
+            assert (3,) + s.image_size == v["image_shape"] and s.flip == ("HFlipTransform" in v["transforms"])
+            out = s.apply_image(img.copy())
+            chw = torch.from_numpy(out.transpose(2, 0, 1).copy())
+            assert hashlib.sha1(chw.numpy().tobytes()).hexdigest() == v["image_sha1"], c["name"]
+    assert resize_shortest_edge(375, 500, 480, 4000) == (480, 640)
+    assert resize_shortest_edge(500, 375, 1152, 1200) == (1200, 900)
+    p = ViewSpec(375, 500, 480, 640, True, orig_hw=(750, 1000)).params(batch_index=1.0)
+    assert p == [640 / 500, 480 / 375, 1.0, 640.0, 480.0, 1.0, 500 / 640, 375 / 480, 2.0, 2.0]
+    assert len(ViewSpec(10, 10, 20, 20, False).params()) == 10

@@ -191,3 +191,57 @@ def test_voc_writer_rows_and_tta_inverse():
     b = torch.tensor([[10.0, 5.0, 30.0, 25.0]])
     out = ref.tta_inverse_boxes(b, 0.5, 0.5, True, 100)
     assert torch.equal(out, torch.tensor([[35.0, 2.5, 45.0, 12.5]]))
+
+
+# ---------------------------------------------------------------- (d) test-time augmentation (row U) vs the reference
+TTA_GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "tta_golden.pt")
+
+
+@pytest.fixture(scope="module")
+def tta_gold():
+    return torch.load(TTA_GOLDEN, weights_only=False)
+
+
+def _tta_post(c):
+    (h, w), (dh, dw) = c["stored_hw"], c["dataset_hw"]
+    return None if (h, w) == (dh, dw) else (dw * 1.0 / w, dh * 1.0 / h)
+
+
+def test_tta_views_match_reference_mapper(tta_gold):
+    """DatasetMapperTTAAVG.__call__ of the reference: view order, sizes and the transformed proposals, bit for bit."""
+    for c in tta_gold["cases"]:
+        h, w = c["stored_hw"]
+        sizes = ref.tta_view_sizes(h, w, c["min_sizes"], c["max_size"], c["flip"])
+        assert len(sizes) == len(c["views"]), c["name"]
+        boxes = c["boxes"][: c["topk"]]
+        for (nh, nw, fl), v in zip(sizes, c["views"]):
+            assert v["image_shape"] == (3, nh, nw) and v["image_size"] == (nh, nw)
+            assert ("HFlipTransform" in v["transforms"]) == fl
+            b, keep = ref.tta_transform_proposals(boxes, (h, w), (nh, nw), fl)
+            assert bool(keep.all())
+            assert torch.equal(b, v["proposal_boxes"]), c["name"]
+            assert torch.equal(c["obj"][: c["topk"]], v["objectness_logits"])
+
+
+def test_tta_merge_and_detections_match_reference(tta_gold):
+    """GeneralizedRCNNWithTTAAVG._get_augmented_boxes / _merge_detections of the reference, bit for bit."""
+    for c in tta_gold["cases"]:
+        h, w = c["stored_hw"]
+        C = c["C"]
+        sizes = ref.tta_view_sizes(h, w, c["min_sizes"], c["max_size"], c["flip"])
+        eb = [ref.tta_inverse_boxes(c["view_boxes"][i].reshape(-1, 4), w * 1.0 / nw, h * 1.0 / nh, fl, nw, _tta_post(c))
+              .reshape(-1, 4 * C) for i, (nh, nw, fl) in enumerate(sizes)]
+        mb, mp = ref.tta_merge(eb, [c["view_scores"][i] for i in range(len(sizes))])
+        assert torch.equal(mb, c["merged_boxes"]) and torch.equal(mp, c["merged_scores"]), c["name"]
+        db, ds, dc, _ = ref.fast_rcnn_inference_single_image(mb, mp, c["dataset_hw"], 1e-6, 0.3, 100)
+        assert torch.equal(db, c["det_boxes"]) and torch.equal(ds, c["det_scores"]) and torch.equal(dc, c["det_classes"])
+
+
+def test_tta_transform_edge_cases():
+    # malformed (x2 < x1) boxes come out ordered (corner min / max); boxes outside the view are clipped to empty
+    b = torch.tensor([[30.0, 10.0, 10.0, 40.0], [-50.0, -50.0, -10.0, -5.0], [5.0, 5.0, 5.0, 30.0]])
+    out, keep = ref.tta_transform_proposals(b, (60, 80), (120, 160), True)
+    assert torch.equal(out[0], torch.tensor([100.0, 20.0, 140.0, 80.0]))
+    assert keep.tolist() == [True, False, False]
+    out2, keep2 = ref.tta_transform_proposals(b[:1], (60, 80), (120, 160), False, min_box_size=40.0)
+    assert keep2.tolist() == [False] and torch.equal(out2[0], torch.tensor([20.0, 20.0, 60.0, 80.0]))
