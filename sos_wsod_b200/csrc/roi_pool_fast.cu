@@ -757,36 +757,55 @@ static int launch_bwd_fast_t(const void* grad, long long ld_grad, const uint16_t
 }
 
 // ------------------------------------------------------------------------------------------------
-// backward, queued (v8): the read-add-write chain of a plane pair is the critical path of this kernel (the steps of
-// one roi and of consecutive rois may touch the same cell, so they run in order), and every cycle a chain spends on
-// anything else -- preparing operands, probing an mbarrier (90-150 cycles per probe), handing a token to the next
-// warp -- is lost.  Here each plane pair has ONE accumulator warp that does nothing but the chain, fed through a
-// shared-memory queue by P preparation warps:
+// backward, queued (v8).  Measured on the turn-token kernel above (ncu, per-instruction samples): the ordered
+// read-add-write chain of a plane pair costs ~200 cycles per roi, everything around it (operand preparation, token
+// hand-off, barrier probes at 90-150 cycles each) another ~400.  Here every plane pair has ONE accumulator warp that
+// does nothing but consume a stream of ready-made steps, fed through a shared-memory queue:
 //
-//   TMA warp      as above: streams [RT rois x BW columns] tiles of arg-max / grad_out through the mbarrier ring.
-//   prep warps    P per plane pair, rois dealt round-robin.  A prep warp turns its roi into up to 4 colour steps of
-//                 32 (shared address, scaled gradient) pairs and stores them as 64-bit entries into its queue slot;
-//                 rois with more than 4 colour steps (narrower than 7 cells) send further chunks through the same slot.
-//   accumulator   per roi: loads its slot's 4 x 32 entries (prefetched while the previous roi accumulates), checks
-//                 the tag every entry carries, releases the slot, runs the 4 ordered read-add-write steps.
+//   TMA warp      streams [RT rois x BW columns] tiles of arg-max / grad_out through the mbarrier ring and, per roi,
+//                 publishes (scale, colour strides, first chunk number): the rois' colour steps are cut into CHUNKS
+//                 of 4 steps, numbered consecutively over the image's rois (a warp scan per tile), so that the
+//                 accumulator sees one uniform stream.  Plan records are fetched 32 rois at a time, one window ahead.
+//   prep warps    P per plane pair, rois dealt round-robin.  A prep warp turns each chunk of its roi into 4 x 32
+//                 (shared address, scaled gradient) pairs and stores them into queue slot (chunk number mod Q) once
+//                 the accumulator has consumed the slot's previous occupant.
+//   accumulator   chunk by chunk: entries of the next chunk are fetched while the current one accumulates.
 //
-// Queue protocol without fences or mbarriers on the accumulator's path: an entry is ONE 64-bit shared store
-// {address (18 bits) | more << 18 | tag << 19, value}; the tag names the slot's use (round, chunk), so an entry whose
-// tag matches is complete and current.  The slot goes back to its prep warp through a plain token word the
-// accumulator writes after the entries are in its registers (single writer, single reader).
-// Result: deterministic (fixed order per plane), atomic-free, bit-identical to the turn-token kernel above.
-constexpr int kBwdQSteps = 4;                       // colour steps per queue slot
+// Queue protocol, no fences and no mbarriers on the accumulator's path: an entry is ONE 64-bit shared store
+// {address (18 bits) | tag << 19, value}; the tag names the slot's use (chunk number / Q).  A prep warp writes the 4
+// steps of a chunk in order 0..3; the accumulator reads them in order 3..0 and checks step 3's tag in every lane:
+// shared-memory requests of an SM are served in order, so a current step 3 implies current steps 0..2.  Slots return
+// to the prep warps through one counter per plane pair (chunks consumed so far; single writer).
+// Result: deterministic (fixed order per plane), atomic-free, bit-identical to the turn-token kernel.
+constexpr int kBwdQSteps = 4;                       // colour steps per chunk / queue slot
 constexpr int kBwdQSlotBytes = kBwdQSteps * 32 * 8;
 constexpr int kBwdQMaxP = 4;
+constexpr int kBwdQMaxQ = 8;
 
 struct BwdQCfg {
     BwdFastCfg b;
-    int P, D;          // prep warps per plane pair, slots per prep warp (queue depth Q = P * D)
+    int P;             // prep warps per plane pair
+    int LQ;            // log2 of the queue depth Q (slots per plane pair)
 };
 
+struct __align__(16) BwdMetaQ {
+    float scale;
+    int code;    // 0 = roi of another image (no chunks); else 1 | mh << 8 | mw << 16
+    int cbase;   // number of the roi's first chunk in the image's stream
+    int nch;     // its number of chunks
+};
+
+__device__ __forceinline__ int bwdq_chunks_of(uint32_t tail_x, int b) {
+    // tail_x = bytes 56..59 of a RoiRecord: mh | mw << 8 | batch << 16
+    if ((int)(tail_x >> 16) != b) return 0;
+    const int nsteps = (int)(tail_x & 0xFFu) * (int)((tail_x >> 8) & 0xFFu);
+    return (nsteps + kBwdQSteps - 1) / kBwdQSteps;
+}
+
+// steps 3, 2, 1, 0 in that order (see the protocol above)
 __device__ __forceinline__ void q_load(uint32_t qa, uint32_t (&lo)[kBwdQSteps], uint32_t (&hi)[kBwdQSteps]) {
 #pragma unroll
-    for (int k = 0; k < kBwdQSteps; ++k)
+    for (int k = kBwdQSteps - 1; k >= 0; --k)
         asm volatile("ld.volatile.shared.v2.u32 {%0, %1}, [%2];" : "=r"(lo[k]), "=r"(hi[k]) : "r"(qa + 256u * k) : "memory");
 }
 
@@ -799,14 +818,14 @@ roi_pool_bwd_q_kernel(const __grid_constant__ CUtensorMap tmap_arg, const __grid
     extern __shared__ uint8_t smem_raw[];
     const BwdFastCfg& cfg = qc.b;
     const int CT = cfg.CT, BW = cfg.BW, nbox = cfg.nbox, S = cfg.stages, RT = cfg.RT;
-    const int P = qc.P, D = qc.D, Q = P * D;
+    const int P = qc.P, LQ = qc.LQ, Q = 1 << LQ;
     const int NP = (CT + 1) >> 1;   // plane pairs = accumulator warps
     const int NPREP = NP * P;
     const uint32_t base = (smem_u32(smem_raw) + 127u) & ~127u;
     uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
     float* planes = reinterpret_cast<float*>(gen_base);                          // [CT][plane_stride]
     const uint32_t plane_bytes = (uint32_t)CT * cfg.plane_stride * 4;            // multiple of 128
-    const uint32_t arg_box = (uint32_t)RT * BW * 2;
+    const uint32_t arg_box = (uint32_t)RT * BW * 2;                              // multiples of 128 (RT >= 8)
     const uint32_t grad_box = (uint32_t)RT * BW * sizeof(GradT);
     const uint32_t arg_stage = nbox * arg_box, grad_stage = nbox * grad_box;
     const uint32_t ring_off = plane_bytes;
@@ -814,10 +833,11 @@ roi_pool_bwd_q_kernel(const __grid_constant__ CUtensorMap tmap_arg, const __grid
     const uint32_t bar_off = queue_off + (uint32_t)NP * Q * kBwdQSlotBytes;
     auto full_bar = [&](int st) { return base + bar_off + 8u * st; };
     auto empty_bar = [&](int st) { return base + bar_off + 8u * (S + st); };
-    const uint32_t token_off = bar_off + 16u * S;                                // [NP][Q] uint32 slot tokens
-    const uint32_t meta_off = token_off + 4u * (kBwdFastMaxCT / 2) * (kBwdQMaxP * 2);
-    BwdMeta* s_meta = reinterpret_cast<BwdMeta*>(gen_base + meta_off);           // [S][kBwdFastMaxRT]
+    const uint32_t cons_off = bar_off + 16u * S;                                 // [NP] chunks consumed, [NP] = total
+    const uint32_t meta_off = cons_off + 4u * (kBwdFastMaxCT / 2 + 4);           // 16-byte aligned
+    BwdMetaQ* s_meta = reinterpret_cast<BwdMetaQ*>(gen_base + meta_off);         // [S][kBwdFastMaxRT]
     float* s_dummy = reinterpret_cast<float*>(s_meta + S * kBwdFastMaxRT);        // [32] idle-lane targets
+    int* s_total = reinterpret_cast<int*>(gen_base + cons_off) + kBwdFastMaxCT / 2;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int groups = (C + CT - 1) / CT;
@@ -833,7 +853,7 @@ roi_pool_bwd_q_kernel(const __grid_constant__ CUtensorMap tmap_arg, const __grid
     for (int i = threadIdx.x; i < CT * cfg.plane_stride; i += blockDim.x) planes[i] = 0.f;
     {
         uint32_t* z = reinterpret_cast<uint32_t*>(gen_base + queue_off);
-        const int nz = (int)((meta_off - queue_off) / 4);      // queue entries (tag 0 = invalid), barriers, tokens
+        const int nz = (int)((meta_off - queue_off) / 4);      // queue entries (tag 0 = invalid), barriers, counters
         for (int i = threadIdx.x; i < nz; i += blockDim.x) z[i] = 0u;
     }
     __syncthreads();
@@ -844,12 +864,22 @@ roi_pool_bwd_q_kernel(const __grid_constant__ CUtensorMap tmap_arg, const __grid
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    __syncthreads();
+    // rows of this image: the plan's order is stable, so its first / last entries are the smallest / largest row
     const int seg_lo = img_start[b], seg_hi = img_start[b + 1];
     const int r_lo = seg_hi > seg_lo ? __ldg(order + seg_lo) : 0;
     const int r_hi = seg_hi > seg_lo ? __ldg(order + seg_hi - 1) + 1 : 0;
     const int nrois = r_hi - r_lo;
     const int ntiles = (nrois + RT - 1) / RT;
+    {
+        // length of the image's chunk stream (the accumulators' trip count)
+        int mine = 0;
+        for (int i = threadIdx.x; i < nrois; i += blockDim.x)
+            mine += bwdq_chunks_of(__ldg(reinterpret_cast<const uint32_t*>(rec + r_lo + i) + 14), b);
+        mine = warp_sum_int(mine);
+        if (lane == 0 && mine) atomicAdd(s_total, mine);   // integer bookkeeping
+    }
+    __syncthreads();
+    const int total_chunks = *s_total;
     const int total_cols = C * PP;
     const int col0 = c0 * PP;
     const int col_a = col0 & ~7;
@@ -862,20 +892,39 @@ roi_pool_bwd_q_kernel(const __grid_constant__ CUtensorMap tmap_arg, const __grid
             if (col_a + bx * BW < total_cols) tx += arg_box;
             if (col_g + bx * BW < total_cols) tx += grad_box;
         }
+        // plan records (bytes 56..63) of a window of 32 rois per lane, the next window already in flight
+        auto fetch = [&](int w0) {
+            uint2 v = make_uint2(0xFFFF0000u, 0u);      // batch 0xFFFF: no image
+            if (w0 + lane < nrois) v = __ldg(reinterpret_cast<const uint2*>(rec + r_lo + w0 + lane) + 7);
+            return v;
+        };
+        int win = 0;
+        uint2 cur = fetch(0), nxt = fetch(32);
+        int running = 0;
         int st = 0;
         uint32_t phase = 0;
         for (int t = 0; t < ntiles; ++t) {
-            const int r0 = r_lo + t * RT;
-            BwdMeta meta;
-            meta.scale = 0.f;
-            meta.code = 0;
-            if (lane < RT && r0 + lane < r_hi) {
-                const uint2 tail = __ldg(reinterpret_cast<const uint2*>(rec + r0 + lane) + 7);   // bytes 56..63
-                if ((int)(tail.x >> 16) == b) {
-                    meta.scale = __uint_as_float(tail.y);
-                    meta.code = 1 | ((tail.x & 0xFFu) << 8) | (((tail.x >> 8) & 0xFFu) << 16);
-                }
+            const int r0 = t * RT;
+            if (r0 >= win + 32) {
+                win += 32;
+                cur = nxt;
+                nxt = fetch(win + 32);
             }
+            const int src = r0 - win + lane;               // RT divides 32: a tile never straddles two windows
+            const uint32_t tail_x = __shfl_sync(FULL_MASK, cur.x, src & 31);
+            const uint32_t tail_y = __shfl_sync(FULL_MASK, cur.y, src & 31);
+            BwdMetaQ meta;
+            meta.scale = __uint_as_float(tail_y);
+            meta.nch = (lane < RT && r0 + lane < nrois) ? bwdq_chunks_of(tail_x, b) : 0;
+            meta.code = meta.nch ? (int)(1u | ((tail_x & 0xFFu) << 8) | (((tail_x >> 8) & 0xFFu) << 16)) : 0;
+            int incl = meta.nch;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int up = __shfl_up_sync(FULL_MASK, incl, o);
+                if (lane >= o) incl += up;
+            }
+            meta.cbase = running + incl - meta.nch;
+            running += __shfl_sync(FULL_MASK, incl, 31);
             mbar_wait(empty_bar(st), phase ^ 1u);
             if (lane < RT) s_meta[st * kBwdFastMaxRT + lane] = meta;
             __syncwarp();
@@ -884,8 +933,8 @@ roi_pool_bwd_q_kernel(const __grid_constant__ CUtensorMap tmap_arg, const __grid
                 const uint32_t sa = base + ring_off + st * (arg_stage + grad_stage);
                 const uint32_t sg = sa + arg_stage;
                 for (int bx = 0; bx < nbox; ++bx) {
-                    if (col_a + bx * BW < total_cols) tma_load_2d(sa + bx * arg_box, &tmap_arg, full_bar(st), col_a + bx * BW, r0);
-                    if (col_g + bx * BW < total_cols) tma_load_2d(sg + bx * grad_box, &tmap_grad, full_bar(st), col_g + bx * BW, r0);
+                    if (col_a + bx * BW < total_cols) tma_load_2d(sa + bx * arg_box, &tmap_arg, full_bar(st), col_a + bx * BW, r_lo + r0);
+                    if (col_g + bx * BW < total_cols) tma_load_2d(sg + bx * grad_box, &tmap_grad, full_bar(st), col_g + bx * BW, r_lo + r0);
                 }
             }
             if (++st == S) {
@@ -895,54 +944,32 @@ roi_pool_bwd_q_kernel(const __grid_constant__ CUtensorMap tmap_arg, const __grid
         }
     } else if (warp < NP) {
         // ---- accumulator warp of plane pair `warp` ----
-        const int pair = warp;
-        const uint32_t qbase = base + queue_off + (uint32_t)pair * Q * kBwdQSlotBytes + 8u * lane;
-        const uint32_t tok_s = base + token_off + 4u * (pair * Q);
-        uint32_t lo[kBwdQSteps], hi[kBwdQSteps], nlo[kBwdQSteps], nhi[kBwdQSteps];
-        int s = 0, round = 0;
-        if (nrois > 0) q_load(qbase, lo, hi);
-        for (int r = 0; r < nrois; ++r) {
-            const uint32_t qa = qbase + (uint32_t)s * kBwdQSlotBytes;
-            int ns = s + 1, nround = round;
-            if (ns == Q) {
-                ns = 0;
-                ++nround;
-            }
-            int k = 0;
-            while (true) {
-                const uint32_t tag = 0x1000u | (((uint32_t)round & 0xFFu) << 4) | (uint32_t)k;
-                while (true) {
-                    bool ok = true;
-#pragma unroll
-                    for (int i = 0; i < kBwdQSteps; ++i) ok = ok && (lo[i] >> 19) == tag;
-                    if (__all_sync(FULL_MASK, ok)) break;
-                    q_load(qa, lo, hi);
-                }
-                const bool more = (lo[0] >> 18) & 1u;
-                // the entries are in registers: hand the slot back, then start fetching the next roi's slot
-                if (lane == 0)
-                    asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(tok_s + 4u * s), "r"((((uint32_t)r << 4) | (uint32_t)k) + 1u) : "memory");
-                if (!more && r + 1 < nrois) q_load(qbase + (uint32_t)ns * kBwdQSlotBytes, nlo, nhi);
-#pragma unroll
-                for (int i = 0; i < kBwdQSteps; ++i) {
-                    const uint32_t ad = lo[i] & 0x3FFFFu;
-                    float v;
-                    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(ad) : "memory");
-                    v += __uint_as_float(hi[i]);
-                    asm volatile("st.shared.f32 [%0], %1;" ::"r"(ad), "f"(v) : "memory");
-                    __syncwarp();   // colour classes of one roi may share cells: order the steps
-                }
-                if (!more) break;
-                ++k;
-                q_load(qa, lo, hi);
-            }
+        const uint32_t qbase = base + queue_off + (uint32_t)warp * Q * kBwdQSlotBytes + 8u * lane;
+        const uint32_t cons_s = base + cons_off + 4u * warp;
+        const uint32_t qmask = (uint32_t)Q - 1u;
+        // one chunk: wait until it is complete, give its slot back, start fetching chunk seq + 1 into (nlo, nhi), then
+        // run the ordered steps
+        auto consume = [&](uint32_t seq, uint32_t (&lo)[kBwdQSteps], uint32_t (&hi)[kBwdQSteps], uint32_t (&nlo)[kBwdQSteps],
+                           uint32_t (&nhi)[kBwdQSteps]) {
+            const uint32_t tag = 0x1000u | ((seq >> LQ) & 0xFFFu);
+            while (!__all_sync(FULL_MASK, (lo[kBwdQSteps - 1] >> 19) == tag)) q_load(qbase + (seq & qmask) * kBwdQSlotBytes, lo, hi);
+            if (lane == 0) asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(cons_s), "r"(seq + 1u) : "memory");
+            if (seq + 1u < (uint32_t)total_chunks) q_load(qbase + ((seq + 1u) & qmask) * kBwdQSlotBytes, nlo, nhi);
 #pragma unroll
             for (int i = 0; i < kBwdQSteps; ++i) {
-                lo[i] = nlo[i];
-                hi[i] = nhi[i];
+                const uint32_t ad = lo[i] & 0x3FFFFu;
+                float v;
+                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(ad) : "memory");
+                v += __uint_as_float(hi[i]);
+                asm volatile("st.shared.f32 [%0], %1;" ::"r"(ad), "f"(v) : "memory");
+                __syncwarp();   // colour classes of one roi may share cells: order the steps
             }
-            s = ns;
-            round = nround;
+        };
+        uint32_t alo[kBwdQSteps], ahi[kBwdQSteps], blo[kBwdQSteps], bhi[kBwdQSteps];
+        if (total_chunks > 0) q_load(qbase, alo, ahi);
+        for (uint32_t seq = 0; seq < (uint32_t)total_chunks; seq += 2) {
+            consume(seq, alo, ahi, blo, bhi);
+            if (seq + 1u < (uint32_t)total_chunks) consume(seq + 1u, blo, bhi, alo, ahi);
         }
     } else {
         // ---- preparation warp j of plane pair `pair` ----
@@ -956,11 +983,12 @@ roi_pool_bwd_q_kernel(const __grid_constant__ CUtensorMap tmap_arg, const __grid
         const int ea0 = chan * PP + (col0 - col_a);
         const int eg0 = chan * PP + (col0 - col_g);
         const unsigned band_cells = (unsigned)(band_hi - band_lo);
-        const int wrap = (RT - 1) * BW;
+        const int wrap = (RT - 1) * BW;          // elements skipped when an entry falls into the second box
         const uint32_t ring_s = base + ring_off;
         const uint32_t stage_bytes = arg_stage + grad_stage;
         const uint32_t qpair = base + queue_off + (uint32_t)pair * Q * kBwdQSlotBytes + 8u * lane;
-        const uint32_t tok_s = base + token_off + 4u * (pair * Q);
+        const uint32_t cons_s = base + cons_off + 4u * pair;
+        const uint32_t qmask = (uint32_t)Q - 1u;
         constexpr int kCode22 = 1 | (2 << 8) | (2 << 16);
         int e22a[4], e22g[4];
         bool v22[4];
@@ -973,9 +1001,6 @@ roi_pool_bwd_q_kernel(const __grid_constant__ CUtensorMap tmap_arg, const __grid
             e = eg0 + ph * kPlanP + pw;
             e22g[k] = e + (e >= BW ? wrap : 0);
         }
-        uint32_t last_tok[2] = {0u, 0u};   // last token written per own slot (D <= 2)
-        int d = 0;                          // own slot counter: slot = j + d * P
-        int round = 0;                      // r / Q of the current roi
         int st = 0;
         uint32_t phase = 0;
         int r = j;
@@ -984,18 +1009,16 @@ roi_pool_bwd_q_kernel(const __grid_constant__ CUtensorMap tmap_arg, const __grid
             // every prep warp waits for every tile, also one that holds none of its rois: its arrival on the empty
             // barrier must not run ahead into the stage's previous phase
             mbar_wait(full_bar(st), phase);
-            const uint32_t sa = ring_s + st * stage_bytes;
-            const uint32_t sg = sa + arg_stage;
-            const BwdMeta* metas = s_meta + st * kBwdFastMaxRT;
+            const uint32_t sa = ring_s + st * stage_bytes;      // arg-max boxes of this stage
+            const uint32_t sg = sa + arg_stage;                 // grad boxes
+            const BwdMetaQ* metas = s_meta + st * kBwdFastMaxRT;
             for (; r < tile_end; r += P) {
                 const int rr = r - t * RT;
-                const BwdMeta m = metas[rr];
+                const BwdMetaQ m = metas[rr];
+                if (m.nch == 0) continue;                       // roi of another image
                 const int mh = (m.code >> 8) & 0xFF, mw = (m.code >> 16) & 0xFF;
-                const int nsteps = mh * mw;                     // 0 for a roi of another image
+                const int nsteps = mh * mw;
                 const int rowe = rr * BW;
-                const int slot = j + d * P;
-                const uint32_t qa = qpair + (uint32_t)slot * kBwdQSlotBytes;
-                const uint32_t tka = tok_s + 4u * slot;
                 auto operand = [&](int ea, int eg, uint32_t& ad, uint32_t& vl) {
                     unsigned a, graw;
                     asm volatile("ld.shared.u16 %0, [%1];" : "=r"(a) : "r"(sa + 2u * (unsigned)(ea + rowe)));
@@ -1010,34 +1033,34 @@ roi_pool_bwd_q_kernel(const __grid_constant__ CUtensorMap tmap_arg, const __grid
                     ad = ok ? my_s + 4u * rel : dummy_s;
                     vl = ok ? __float_as_uint(__uint_as_float(graw) * m.scale) : 0u;
                 };
-                auto publish = [&](const uint32_t (&ad)[kBwdQSteps], const uint32_t (&vl)[kBwdQSteps], int k, bool more) {
-                    const uint32_t want = d ? last_tok[1] : last_tok[0];
-                    uint32_t seen;
-                    do {
-                        asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(seen) : "r"(tka) : "memory");
-                    } while (seen != want);
-                    const uint32_t hdr = ((0x1000u | (((uint32_t)round & 0xFFu) << 4) | (uint32_t)k) << 19) | (more ? (1u << 18) : 0u);
+                auto publish = [&](const uint32_t (&ad)[kBwdQSteps], const uint32_t (&vl)[kBwdQSteps], uint32_t seq) {
+                    uint32_t consumed;
+                    do {   // the slot's previous occupant is chunk seq - Q
+                        asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(consumed) : "r"(cons_s) : "memory");
+                    } while ((int)(seq - consumed) >= Q);
+                    const uint32_t hdr = (0x1000u | ((seq >> LQ) & 0xFFFu)) << 19;
+                    const uint32_t qa = qpair + (seq & qmask) * kBwdQSlotBytes;
 #pragma unroll
                     for (int i = 0; i < kBwdQSteps; ++i)
                         asm volatile("st.volatile.shared.v2.u32 [%0], {%1, %2};" ::"r"(qa + 256u * i), "r"(ad[i] | hdr), "r"(vl[i]) : "memory");
-                    const uint32_t tok = (((uint32_t)r << 4) | (uint32_t)k) + 1u;
-                    if (d) last_tok[1] = tok; else last_tok[0] = tok;
                 };
                 uint32_t ad[kBwdQSteps], vl[kBwdQSteps];
                 if (m.code == kCode22) {
+                    // strides 2 x 2 (every roi at least 7 x 7 cells): one chunk, the lane's four bins at constant offsets
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
                         ad[k] = dummy_s;
                         vl[k] = 0u;
                         if (v22[k]) operand(e22a[k], e22g[k], ad[k], vl[k]);
                     }
-                    publish(ad, vl, 0, false);
-                } else if (nsteps > 0) {
+                    publish(ad, vl, (uint32_t)m.cbase);
+                } else {
                     const int bin0 = la * mh * kPlanP + lb * mw;
                     const int ih = chan_ok ? min(mh, kPlanP - la * mh) : 0;   // <= 0: block outside the grid
                     const int jw = min(mw, kPlanP - lb * mw);
-                    int i = 0, jj = 0, kchunk = 0;
-                    for (int s0 = 0; s0 < nsteps; s0 += kBwdQSteps, ++kchunk) {
+                    int i = 0, jj = 0;
+                    uint32_t seq = (uint32_t)m.cbase;
+                    for (int s0 = 0; s0 < nsteps; s0 += kBwdQSteps, ++seq) {
                         const int n = min(kBwdQSteps, nsteps - s0);
 #pragma unroll
                         for (int k = 0; k < kBwdQSteps; ++k) {
@@ -1057,19 +1080,8 @@ roi_pool_bwd_q_kernel(const __grid_constant__ CUtensorMap tmap_arg, const __grid
                                 }
                             }
                         }
-                        publish(ad, vl, kchunk, s0 + kBwdQSteps < nsteps);
+                        publish(ad, vl, seq);
                     }
-                } else {
-#pragma unroll
-                    for (int k = 0; k < kBwdQSteps; ++k) {
-                        ad[k] = dummy_s;
-                        vl[k] = 0u;
-                    }
-                    publish(ad, vl, 0, false);
-                }
-                if (++d == D) {
-                    d = 0;
-                    ++round;
                 }
             }
             __syncwarp();
@@ -1089,10 +1101,17 @@ roi_pool_bwd_q_kernel(const __grid_constant__ CUtensorMap tmap_arg, const __grid
     }
 }
 
+static int env_int(const char* name, int dflt) {
+    const char* e = getenv(name);
+    return e ? atoi(e) : dflt;
+}
+
 static bool pick_bwd_q_cfg(int n, int c, int h, int w, int grad_bytes, BwdQCfg* out) {
     const int max_smem = device_max_smem();
     const int sms = device_num_sms();
     const int align_elems = 16 / (2 < grad_bytes ? 2 : grad_bytes);
+    // tuning overrides (0 = let the search decide)
+    const int force_p = env_int("SOSWSOD_BWDQ_P", 0), force_lq = env_int("SOSWSOD_BWDQ_LQ", 0);
     bool found = false;
     double best_cost = 0;
     for (int bands = 1; bands <= 64; ++bands) {
@@ -1102,14 +1121,15 @@ static bool pick_bwd_q_cfg(int n, int c, int h, int w, int grad_bytes, BwdQCfg* 
         for (int CT = kBwdFastMaxCT; CT >= 1; --CT) {
             if (CT > c) continue;
             const int NP = (CT + 1) / 2;
-            const int cols = CT * kPP + align_elems - 1;
+            const int cols = CT * kPP + align_elems - 1;   // + the alignment remainder of the first column
             const int nbox = (cols + 247) / 248;
             const int BW = (((cols + nbox - 1) / nbox) + 7) / 8 * 8;
             if (BW > 256 || nbox > 2) continue;
             for (int P = kBwdQMaxP; P >= 2; --P)
-                for (int D = 2; D >= 1; --D) {
-                    const size_t fixed = (size_t)CT * plane_stride * 4 + (size_t)NP * P * D * kBwdQSlotBytes + 128 /*align*/ +
-                                         1792 /*barriers, tokens, roi meta, dummies*/;
+                for (int LQ = 3; LQ >= 1; --LQ) {
+                    if ((force_p && P != force_p) || (force_lq && LQ != force_lq)) continue;
+                    const size_t fixed = (size_t)CT * plane_stride * 4 + (size_t)NP * (1 << LQ) * kBwdQSlotBytes + 128 /*align*/ +
+                                         2304 /*barriers, counters, roi meta, dummies*/;
                     for (int RT = kBwdFastMaxRT; RT >= 8; RT >>= 1) {   // RT * BW * 2 bytes per box: a multiple of 128
                         const size_t stage = (size_t)nbox * RT * BW * (2 + grad_bytes);
                         if (fixed + 2 * stage > (size_t)max_smem) continue;
@@ -1118,9 +1138,9 @@ static bool pick_bwd_q_cfg(int n, int c, int h, int w, int grad_bytes, BwdQCfg* 
                         const long long ctas = (long long)n * ((c + CT - 1) / CT) * bands;
                         const long long waves = (ctas + sms - 1) / sms;
                         // time ~ waves (every CTA streams all rois of its image; its chains advance together); then
-                        // prefer enough prep warps and queue depth to keep the accumulators fed, then a deeper ring
-                        const double cost = (double)waves + 0.02 * (kBwdQMaxP - P) + (D < 2 ? 0.01 : 0.0) +
-                                            (stages < 3 ? 0.005 : 0.0) + ((CT & 1) ? 0.01 : 0.0);
+                        // enough prep warps and queue slots to keep the accumulators fed, then a ring of >= 3 stages
+                        const double cost = (double)waves + 0.02 * (kBwdQMaxP - P) + 0.01 * (3 - LQ) +
+                                            (stages < 3 ? 0.015 : 0.0) + ((CT & 1) ? 0.01 : 0.0);
                         if (!found || cost < best_cost - 1e-9) {
                             found = true;
                             best_cost = cost;
@@ -1134,7 +1154,7 @@ static bool pick_bwd_q_cfg(int n, int c, int h, int w, int grad_bytes, BwdQCfg* 
                             out->b.plane_stride = plane_stride;
                             out->b.smem = fixed + (size_t)stages * stage;
                             out->P = P;
-                            out->D = D;
+                            out->LQ = LQ;
                         }
                         if (stages >= 3) break;
                     }
