@@ -779,7 +779,7 @@ static int launch_bwd_fast_t(const void* grad, long long ld_grad, const uint16_t
 // Result: deterministic (fixed order per plane), atomic-free, bit-identical to the turn-token kernel.
 constexpr int kBwdQSteps = 4;                       // colour steps per chunk / queue slot
 constexpr int kBwdQSlotBytes = kBwdQSteps * 32 * 8;
-constexpr int kBwdQMaxP = 4;
+constexpr int kBwdQMaxP = 6;
 constexpr int kBwdQMaxQ = 8;
 
 struct BwdQCfg {
@@ -949,27 +949,38 @@ roi_pool_bwd_q_kernel(const __grid_constant__ CUtensorMap tmap_arg, const __grid
         const uint32_t qmask = (uint32_t)Q - 1u;
         // one chunk: wait until it is complete, give its slot back, start fetching chunk seq + 1 into (nlo, nhi), then
         // run the ordered steps
-        auto consume = [&](uint32_t seq, uint32_t (&lo)[kBwdQSteps], uint32_t (&hi)[kBwdQSteps], uint32_t (&nlo)[kBwdQSteps],
-                           uint32_t (&nhi)[kBwdQSteps]) {
-            const uint32_t tag = 0x1000u | ((seq >> LQ) & 0xFFFu);
-            while (!__all_sync(FULL_MASK, (lo[kBwdQSteps - 1] >> 19) == tag)) q_load(qbase + (seq & qmask) * kBwdQSlotBytes, lo, hi);
+        // one chunk: (wait until it is complete,) give its slot back, start fetching chunk seq + 1 into (nlo, nhi), run the
+        // ordered steps; the next chunk's tag check rides in the shadow of the chain's shared-memory latencies
+        auto consume = [&](uint32_t seq, bool valid, uint32_t (&lo)[kBwdQSteps], uint32_t (&hi)[kBwdQSteps],
+                           uint32_t (&nlo)[kBwdQSteps], uint32_t (&nhi)[kBwdQSteps]) -> bool {
+            if (!valid) {
+                const uint32_t tag = 0x1000u | ((seq >> LQ) & 0xFFFu);
+                do {
+                    q_load(qbase + (seq & qmask) * kBwdQSlotBytes, lo, hi);
+                } while (!__all_sync(FULL_MASK, (lo[kBwdQSteps - 1] >> 19) == tag));
+            }
             if (lane == 0) asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(cons_s), "r"(seq + 1u) : "memory");
-            if (seq + 1u < (uint32_t)total_chunks) q_load(qbase + ((seq + 1u) & qmask) * kBwdQSlotBytes, nlo, nhi);
+            const bool have_next = seq + 1u < (uint32_t)total_chunks;
+            if (have_next) q_load(qbase + ((seq + 1u) & qmask) * kBwdQSlotBytes, nlo, nhi);
+            const uint32_t ntag = 0x1000u | (((seq + 1u) >> LQ) & 0xFFFu);
+            bool nvalid = false;
 #pragma unroll
             for (int i = 0; i < kBwdQSteps; ++i) {
                 const uint32_t ad = lo[i] & 0x3FFFFu;
                 float v;
                 asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(ad) : "memory");
+                if (i == 1) nvalid = __all_sync(FULL_MASK, have_next && (nlo[kBwdQSteps - 1] >> 19) == ntag);
                 v += __uint_as_float(hi[i]);
                 asm volatile("st.shared.f32 [%0], %1;" ::"r"(ad), "f"(v) : "memory");
                 __syncwarp();   // colour classes of one roi may share cells: order the steps
             }
+            return nvalid;
         };
         uint32_t alo[kBwdQSteps], ahi[kBwdQSteps], blo[kBwdQSteps], bhi[kBwdQSteps];
-        if (total_chunks > 0) q_load(qbase, alo, ahi);
+        bool valid = false;
         for (uint32_t seq = 0; seq < (uint32_t)total_chunks; seq += 2) {
-            consume(seq, alo, ahi, blo, bhi);
-            if (seq + 1u < (uint32_t)total_chunks) consume(seq + 1u, blo, bhi, alo, ahi);
+            valid = consume(seq, valid, alo, ahi, blo, bhi);
+            if (seq + 1u < (uint32_t)total_chunks) valid = consume(seq + 1u, valid, blo, bhi, alo, ahi);
         }
     } else {
         // ---- preparation warp j of plane pair `pair` ----
@@ -1139,7 +1150,7 @@ static bool pick_bwd_q_cfg(int n, int c, int h, int w, int grad_bytes, BwdQCfg* 
                         const long long waves = (ctas + sms - 1) / sms;
                         // time ~ waves (every CTA streams all rois of its image; its chains advance together); then
                         // enough prep warps and queue slots to keep the accumulators fed, then a ring of >= 3 stages
-                        const double cost = (double)waves + 0.02 * (kBwdQMaxP - P) + 0.01 * (3 - LQ) +
+                        const double cost = (double)waves + 0.02 * abs(4 - P) + 0.01 * (3 - LQ) +
                                             (stages < 3 ? 0.015 : 0.0) + ((CT & 1) ? 0.01 : 0.0);
                         if (!found || cost < best_cost - 1e-9) {
                             found = true;
