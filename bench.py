@@ -419,15 +419,20 @@ def run_b200_arm(args):
     copy_stream = torch.cuda.Stream(device=dev)
     main_stream = torch.cuda.current_stream()
 
+    copy_events = []
+
     def stage_inputs(i):
         im = host[i % n_img]
         with torch.cuda.stream(copy_stream):
+            c0 = torch.cuda.Event(enable_timing=True)
+            c0.record(copy_stream)
             feats = [f.to(dev, non_blocking=True) for f in im["feats"]]
             rois = [r.to(dev, non_blocking=True) for r in im["rois"]]
             obj = im["obj"].to(dev, non_blocking=True)
             gt = im["gt"].to(dev, non_blocking=True)
-            ev = torch.cuda.Event()
+            ev = torch.cuda.Event(enable_timing=True)
             ev.record(copy_stream)
+            copy_events.append((c0, ev))
         for t in feats + rois + [obj, gt]:
             t.record_stream(main_stream)
         return feats, rois, obj, gt, ev
@@ -438,7 +443,10 @@ def run_b200_arm(args):
     loss_bufs = [torch.empty(n_loss, dtype=torch.float32, pin_memory=True) for _ in range(2)]
     pending_loss, host_seen = [], []
 
+    host_time = {"issue": 0.0, "wait": 0.0}
+
     def e2e_step(i, last=False):
+        t_issue = time.perf_counter()
         feats, rois, obj, gt, ev = staged.pop(i) if i in staged else stage_inputs(i)
         if not last:
             staged[i + 1] = stage_inputs(i + 1)
@@ -466,6 +474,8 @@ def run_b200_arm(args):
         ev.record()
         prev = pending_loss.pop() if pending_loss else None
         pending_loss.append((hbuf, ev))
+        t_wait = time.perf_counter()
+        host_time["issue"] += t_wait - t_issue
         if prev is not None:
             prev[1].synchronize()
             host_seen.append(float(prev[0].sum()))
@@ -474,6 +484,7 @@ def run_b200_arm(args):
             host_seen.append(float(hbuf.sum()))
             pending_loss.clear()
             heads.check_deferred(wait=True)
+        host_time["wait"] += time.perf_counter() - t_wait
         return hbuf
 
     for i in range(max(3, args.warmup)):
@@ -484,6 +495,8 @@ def run_b200_arm(args):
     t1 = torch.cuda.Event(enable_timing=True)
     t0.record()
     host_seen.clear()
+    copy_events.clear()
+    host_time["issue"] = host_time["wait"] = 0.0
     for i in range(args.steps):
         hl = e2e_step(i, last=(i == args.steps - 1))
     t1.record()
@@ -496,6 +509,9 @@ def run_b200_arm(args):
     e2e_ms_per_step = float(e2e_ms.item()) / args.steps
     e2e = {"value": world * VIEWS / (e2e_ms_per_step / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
            "d2h_bytes_per_step": int(hl.numel() * 4), "ms_per_step": e2e_ms_per_step,
+           "host_issue_ms_per_step": 1e3 * host_time["issue"] / args.steps,
+           "host_wait_ms_per_step": 1e3 * host_time["wait"] / args.steps,
+           "h2d_copy_ms_per_step": sum(a.elapsed_time(b) for a, b in copy_events) / max(len(copy_events), 1),
            "api": "OICRPlusHeads.forward(images, features, proposals, targets) + sum(losses).backward()",
            "h2d": "pinned host buffers, copied on a side stream one step ahead (double-buffered), inside the timed region",
            "d2h": "each step's loss vector copied to pinned memory behind an event and read on the host one step later"}

@@ -234,8 +234,10 @@ def test_plugin_surface_train_and_eval(cuda_lib):
     out = heads.engine().last_output
     for name, prm in heads.named_parameters():
         assert prm.grad is not None and torch.isfinite(prm.grad).all(), name
-    assert torch.equal(heads.box_head.fc1.weight.grad, out.grads["fc1_w"])
-    assert torch.equal(heads.box_refinery_1.bbox_pred.weight.grad, out.grads["r1_box_w"])
+    # backward hands its gradient buffers to autograd (no clone): the engine keeps losses / aux only
+    assert out.grads == {} and out.grad_feats == [] and "gt_class" in out.aux
+    assert float(heads.box_head.fc1.weight.grad.abs().sum()) > 0
+    assert float(heads.box_refinery_1.bbox_pred.weight.grad.abs().sum()) > 0
     assert f1.grad is not None and f1.grad.shape == f1.shape and float(f1.grad.abs().sum()) > 0
     # an SGD step changes the master weights -> the bf16 operands refresh automatically on the next call
     with torch.no_grad():
