@@ -84,6 +84,9 @@ def synth_views_sizes():
 # ----------------------------------------------------------------------------------------------------
 # clocks sampling
 # ----------------------------------------------------------------------------------------------------
+PRE_WARMUP = 8   # extra untimed steps before the caller's --warmup steps (both timed regions)
+
+
 class ClockSampler:
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -94,9 +97,12 @@ class ClockSampler:
         self.lines = []
 
     def start(self):
+        if os.environ.get("SOSWSOD_NO_SMI"):
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                          "--format=csv,noheader,nounits", "-lms", os.environ.get("SOSWSOD_SMI_MS", "100")],
+                                         stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
@@ -331,7 +337,9 @@ def run_b200_arm(args):
     # ---- device-resident throughput ----
     sampler = ClockSampler(local_rank)
     sampler.start()
-    for i in range(args.warmup):
+    # a fresh box / process runs its first steps slower (lazy module loads, allocator growth, clocks leaving idle):
+    # PRE_WARMUP extra untimed steps come before the W warm-up steps the caller asked for
+    for i in range(PRE_WARMUP + args.warmup):
         device_step(i)
     sampler.wait_first_sample()
     sync_all()
@@ -341,8 +349,16 @@ def run_b200_arm(args):
     t_start = torch.cuda.Event(enable_timing=True)
     t_end = torch.cuda.Event(enable_timing=True)
     t_start.record()
+    # the host stays at most two steps ahead of the device (it issues a step in ~2 ms, the device runs it in ~7 ms):
+    # the same pacing the e2e loop gets from its lagged loss read, without ever starving the device
+    pace = []
     for i in range(args.steps):
-        out = device_step(args.warmup + i)
+        if len(pace) >= 2:
+            pace.pop(0).synchronize()
+        out = device_step(PRE_WARMUP + args.warmup + i)
+        ev = torch.cuda.Event()
+        ev.record()
+        pace.append(ev)
     t_end.record()
     sync_all()
     record_gemm["on"] = False
@@ -488,7 +504,7 @@ def run_b200_arm(args):
         return hbuf
 
     for i in range(max(3, args.warmup)):
-        e2e_step(i, last=(i == max(3, args.warmup) - 1))
+        e2e_step(i, last=(i == max(3, args.warmup) - 1))   # (this region starts warm: it follows the device-resident one)
     staged.clear()
     sync_all()
     t0 = torch.cuda.Event(enable_timing=True)
@@ -539,6 +555,7 @@ def run_b200_arm(args):
                 "config": {"workload": WORKLOAD, "per_gpu": "1 image (4 views) per step", "l2": "per-step working set "
                            "(bf16 pooled operand 401 MB + dgrad 401 MB + fc6 weights/grads 616 MB) >> 126 MB L2; 3 "
                            "distinct synthetic images are cycled", "parallelism": f"dp{world}",
+                           "extra_untimed_warmup_steps": PRE_WARMUP,
                            "allreduce": "NCCL AVG per layer, async, overlapped with the remaining backward" if world > 1 else "none",
                            "fc_flops_per_step": 3 * 2.0 * VIEWS * R_PROPOSALS * (25088 * 4096 + 4096 * 4096)},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
