@@ -334,6 +334,31 @@ def run_b200_arm(args):
             dist.barrier()
             torch.cuda.synchronize()
 
+    def settle(step_fn, block=3, max_blocks=12, tol=0.03):
+        """Untimed: repeats blocks of `block` steps until two consecutive blocks take the same time within `tol` (max
+        over ranks), i.e. until transients that are not ours have died down (the previous process's memory still being
+        scrubbed by the driver, clocks leaving idle).  Every rank takes the same decision.  Returns the blocks run."""
+        prev = None
+        for nb in range(1, max_blocks + 1):
+            a = torch.cuda.Event(enable_timing=True)
+            b = torch.cuda.Event(enable_timing=True)
+            sync_all()
+            a.record()
+            for j in range(block):
+                step_fn(j)
+            b.record()
+            torch.cuda.synchronize()
+            t = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            cur = float(t.item())
+            if prev is not None and abs(cur - prev) <= tol * prev:
+                return nb
+            prev = cur
+        return max_blocks
+
+    eng.fc1_wgrad_panels = int(os.environ.get("SOSWSOD_FC1_PANELS", eng.fc1_wgrad_panels))
+
     # ---- device-resident throughput ----
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -341,6 +366,7 @@ def run_b200_arm(args):
     # PRE_WARMUP extra untimed steps come before the W warm-up steps the caller asked for
     for i in range(PRE_WARMUP + args.warmup):
         device_step(i)
+    settle_blocks = settle(lambda j: device_step(j))
     sampler.wait_first_sample()
     sync_all()
     sampler.mark()
@@ -504,7 +530,8 @@ def run_b200_arm(args):
         return hbuf
 
     for i in range(max(3, args.warmup)):
-        e2e_step(i, last=(i == max(3, args.warmup) - 1))   # (this region starts warm: it follows the device-resident one)
+        e2e_step(i, last=(i == max(3, args.warmup) - 1))
+    settle_blocks_e2e = settle(lambda j: e2e_step(j, last=(j == 2)))
     staged.clear()
     sync_all()
     t0 = torch.cuda.Event(enable_timing=True)
@@ -555,7 +582,8 @@ def run_b200_arm(args):
                 "config": {"workload": WORKLOAD, "per_gpu": "1 image (4 views) per step", "l2": "per-step working set "
                            "(bf16 pooled operand 401 MB + dgrad 401 MB + fc6 weights/grads 616 MB) >> 126 MB L2; 3 "
                            "distinct synthetic images are cycled", "parallelism": f"dp{world}",
-                           "extra_untimed_warmup_steps": PRE_WARMUP,
+                           "extra_untimed_warmup_steps": PRE_WARMUP + 3 * settle_blocks,
+                           "extra_untimed_warmup_steps_e2e": 3 * settle_blocks_e2e,
                            "allreduce": "NCCL AVG per layer, async, overlapped with the remaining backward" if world > 1 else "none",
                            "fc_flops_per_step": 3 * 2.0 * VIEWS * R_PROPOSALS * (25088 * 4096 + 4096 * 4096)},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
@@ -572,7 +600,13 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--shape", default="voc", choices=["voc", "coco"],
+                    help="voc = BASELINE configs[1] (the bench line); coco = configs[3] (80 classes), a side measurement")
     args = ap.parse_args()
+    if args.shape == "coco":
+        global NUM_CLASSES, WORKLOAD
+        NUM_CLASSES = 80
+        WORKLOAD = WORKLOAD.replace("cfg2:", "cfg4:").replace("VOC07 shape", "COCO shape").replace("C=20", "C=80")
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3
     if args.impl == "reference":

@@ -347,3 +347,27 @@ def test_full_size_fc6_against_torch_gemm(cuda_lib):
     y2 = ops.gemm_bf16(a * 2, b, out_dtype=torch.float32)
     y1 = ops.gemm_bf16(a, b, out_dtype=torch.float32)
     assert torch.equal(y2, y1 * 2)
+
+
+def test_grad_hook_panels_are_bit_identical(cuda_lib):
+    """The data-parallel hook path produces fc6's weight gradient in row panels (one hook call per panel, so that each
+    panel's all-reduce can start early): same tiles, bit-identical gradients, hook sees every gradient exactly once."""
+    eng, vb, views, p, gt_classes, cfg = _small_setup(R=200, seed=3)
+    cfg.dropout_p = 0.0
+    gt_int = torch.unique(gt_classes).cuda()
+    ref_out = eng.train_step(vb, gt_int)
+    seen = []
+
+    def hook(name, tensors):
+        seen.append((name, [t.data_ptr() for t in tensors], sum(t.numel() for t in tensors)))
+
+    eng.fc1_wgrad_panels = 4
+    out = eng.train_step(vb, gt_int, grad_hook=hook)
+    for k in ref_out.grads:
+        assert torch.equal(ref_out.grads[k], out.grads[k]), k
+    names = [n for n, _, _ in seen]
+    assert names == ["head", "fc2"] + ["fc1"] * 5
+    fc1_elems = sum(n for name, _, n in seen if name == "fc1")
+    assert fc1_elems == out.grads["fc1_w"].numel() + out.grads["fc1_b"].numel()
+    ptrs = [pp for name, ps, _ in seen if name == "fc1" for pp in ps]
+    assert len(set(ptrs)) == len(ptrs)
