@@ -201,8 +201,11 @@ def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    views, gt, params, r, gflops = cpu_sample_setup(6.0)
-    for _ in range(max(1, min(args.warmup, 2))):
+    # bounded sample: the whole --steps K --warmup W run stays within ~2.5 minutes of host work, one step at most the
+    # full 2000-proposal workload (~7 s on 16 cores)
+    n_warm = max(1, min(args.warmup, 2))
+    views, gt, params, r, gflops = cpu_sample_setup(min(6.0, 150.0 / (args.steps + n_warm)))
+    for _ in range(n_warm):
         cpu_reference_step(views, gt, params)
     t0 = time.perf_counter()
     for _ in range(args.steps):
