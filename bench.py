@@ -327,7 +327,8 @@ def run_b200_arm(args):
     def device_step(i):
         im = dev_imgs[i % n_img]
         vb = ViewBatch(im["feats"], im["rois"], im["obj"], R_PROPOSALS)
-        out = eng.train_step(vb, im["gt"], dropout_seeds=(2 * i + 1, 2 * i + 2), need_feat_grad=True, grad_hook=grad_hook)
+        out = eng.train_step(vb, im["gt"], dropout_seeds=(2 * i + 1, 2 * i + 2), need_feat_grad=True,
+                             grad_hook=grad_hook if world > 1 else None)
         wait_grads()
         return out
 
@@ -454,7 +455,7 @@ def run_b200_arm(args):
     ops.roi_pool_forward, ops.roi_pool_backward = orig_fwd, orig_bwd
 
     # ---- end to end through the plugin surface, host buffers, H2D/D2H inside the timed region ----
-    heads.grad_hook = grad_hook
+    heads.grad_hook = grad_hook if world > 1 else None
     params = [p for p in heads.parameters()]
     h2d = sum(t.numel() * t.element_size() for t in host[0]["feats"] + host[0]["rois"] + [host[0]["obj"]]) + host[0]["gt"].numel() * 8
     image_sizes = [SIZES[0], SIZES[0], SIZES[1], SIZES[1]]
