@@ -84,7 +84,8 @@ def synth_views_sizes():
 # ----------------------------------------------------------------------------------------------------
 # clocks sampling
 # ----------------------------------------------------------------------------------------------------
-PRE_WARMUP = 8   # extra untimed steps before the caller's --warmup steps (both timed regions)
+PRE_WARMUP = int(os.environ.get("SOSWSOD_PRE_WARMUP", "8"))   # extra untimed steps before the caller's --warmup steps
+SETTLE_MAX_BLOCKS = int(os.environ.get("SOSWSOD_SETTLE_BLOCKS", "12"))   # 0 under a profiler (every launch is replayed)
 
 
 class ClockSampler:
@@ -201,10 +202,10 @@ def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    # bounded sample: the whole --steps K --warmup W run stays within ~2.5 minutes of host work, one step at most the
+    # bounded sample: the whole --steps K --warmup W run stays within ~2-3 minutes of host work, one step at most the
     # full 2000-proposal workload (~7 s on 16 cores)
     n_warm = max(1, min(args.warmup, 2))
-    views, gt, params, r, gflops = cpu_sample_setup(min(6.0, 150.0 / (args.steps + n_warm)))
+    views, gt, params, r, gflops = cpu_sample_setup(min(6.0, 100.0 / (args.steps + n_warm)))
     for _ in range(n_warm):
         cpu_reference_step(views, gt, params)
     t0 = time.perf_counter()
@@ -338,7 +339,7 @@ def run_b200_arm(args):
             dist.barrier()
             torch.cuda.synchronize()
 
-    def settle(step_fn, block=3, max_blocks=12, tol=0.03):
+    def settle(step_fn, block=3, max_blocks=SETTLE_MAX_BLOCKS, tol=0.03):
         """Untimed: repeats blocks of `block` steps until two consecutive blocks take the same time within `tol` (max
         over ranks), i.e. until transients that are not ours have died down (the previous process's memory still being
         scrubbed by the driver, clocks leaving idle).  Every rank takes the same decision.  Returns the blocks run."""
