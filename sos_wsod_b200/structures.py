@@ -50,6 +50,10 @@ class Boxes:
         b = self.tensor
         return ((b[:, 2] - b[:, 0]) > threshold) & ((b[:, 3] - b[:, 1]) > threshold)
 
+    def scale(self, scale_x: float, scale_y: float) -> None:
+        self.tensor[:, 0::2] *= scale_x
+        self.tensor[:, 1::2] *= scale_y
+
     def __getitem__(self, item) -> "Boxes":
         if isinstance(item, int):
             return Boxes(self.tensor[item].view(1, -1))
@@ -130,3 +134,19 @@ class ImageList:
 
     def __len__(self) -> int:
         return len(self.image_sizes)
+
+    @staticmethod
+    def from_tensors(tensors, size_divisibility: int = 0, pad_value: float = 0.0) -> "ImageList":
+        """uwsod/detectron2/structures/image_list.py:57-130: pad [C,Hi,Wi] tensors to a common (divisible) size."""
+        assert len(tensors) > 0
+        sizes = [tuple(t.shape[-2:]) for t in tensors]
+        mh, mw = max(s[0] for s in sizes), max(s[1] for s in sizes)
+        if size_divisibility > 1:
+            mh = (mh + size_divisibility - 1) // size_divisibility * size_divisibility
+            mw = (mw + size_divisibility - 1) // size_divisibility * size_divisibility
+        if len(tensors) == 1 and sizes[0] == (mh, mw):
+            return ImageList(tensors[0].unsqueeze(0), sizes)
+        out = tensors[0].new_full((len(tensors),) + tuple(tensors[0].shape[:-2]) + (mh, mw), pad_value)
+        for i, t in enumerate(tensors):
+            out[i, ..., :t.shape[-2], :t.shape[-1]].copy_(t)
+        return ImageList(out, sizes)

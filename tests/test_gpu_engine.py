@@ -371,3 +371,78 @@ def test_grad_hook_panels_are_bit_identical(cuda_lib):
     assert fc1_elems == out.grads["fc1_w"].numel() + out.grads["fc1_b"].numel()
     ptrs = [pp for name, ps, _ in seen if name == "fc1" for pp in ps]
     assert len(set(ptrs)) == len(ptrs)
+
+
+class _TinyBackbone(torch.nn.Module):
+    """conv5 stand-in (stride 8, post-ReLU); the real backbone is the reference's VGG16 on cuDNN."""
+    size_divisibility = 0
+
+    def __init__(self, ch):
+        super().__init__()
+        self.register_buffer("proj", torch.randn((ch, 3, 1, 1), generator=torch.Generator().manual_seed(5)))
+
+    def forward(self, x):
+        x = torch.nn.functional.avg_pool2d(x, 8, ceil_mode=True)
+        return {"plain5": torch.relu(torch.nn.functional.conv2d(x, self.proj))}
+
+
+def test_multi_input_rcnn_mirror(cuda_lib):
+    """MultiInputRCNN (rcnn_multi.py:131-254) around the head: the training forward equals calling the head on the
+    backbone's features directly; inference post-processes to the dataset resolution; the TTA wrapper accepts it."""
+    from sos_wsod_b200.config import get_cfg
+    from sos_wsod_b200.modeling import GeneralizedRCNNWithTTAAVG, MultiInputRCNN, build_roi_heads
+    from sos_wsod_b200.structures import Boxes, Instances, ShapeSpec
+
+    torch.manual_seed(3)
+    cfg = get_cfg()
+    cfg.MODEL.ROI_BOX_HEAD.DAN_DIM = [256, 256]
+    cfg.MODEL.ROI_BOX_HEAD.DROPOUT = 0.0
+    cfg.TEST.AUG.MIN_SIZES, cfg.TEST.AUG.MAX_SIZE = (96, 128), 400
+    ch, C, R = 16, 20, 160
+    heads = build_roi_heads(cfg, {"plain5": ShapeSpec(channels=ch, stride=8)})
+    model = MultiInputRCNN(backbone=_TinyBackbone(ch), proposal_generator=None, roi_heads=heads,
+                           pixel_mean=(102.98, 115.95, 122.77), pixel_std=(1.0, 1.0, 1.0), input_format="BGR").cuda()
+    g = torch.Generator().manual_seed(8)
+    sizes = {"1": (120, 160), "2": (144, 192)}
+    item = {"height": 120, "width": 160}
+    base = ref.synth_boxes(R, 120, 160, g)
+    obj = torch.sort(torch.rand(R, generator=g), descending=True).values
+    for k, (h, w) in sizes.items():
+        img = torch.rand((3, h, w), generator=g) * 255
+        b = base * (h / 120.0)
+        item["image" + k] = img
+        item["image" + k + "_flip"] = img.flip(-1)
+        item["proposals" + k] = Instances((h, w), proposal_boxes=Boxes(b), objectness_logits=obj)
+        item["proposals" + k + "_flip"] = Instances((h, w), proposal_boxes=Boxes(ref.flip_boxes(b, w)), objectness_logits=obj)
+    item["instances1"] = Instances((120, 160), gt_classes=torch.tensor([4, 9]), gt_boxes=Boxes(torch.zeros(2, 4)))
+    model.train()
+    losses = model([item])
+    K = cfg.WSL.REFINE_NUM
+    assert sorted(losses) == sorted(["loss_cls"] + [f"loss_cls_r{k}" for k in range(K)] + [f"loss_box_reg_r{k}" for k in range(K)])
+    sum(losses.values()).backward()
+    assert heads.box_head.fc1.weight.grad is not None
+    # the same step by hand: features from the backbone, the head called directly
+    im1, im2, im1f, im2f = model.preprocess_image([item])
+    f1 = model.backbone(torch.cat([im1.tensor, im1f.tensor], 0))
+    f2 = model.backbone(torch.cat([im2.tensor, im2f.tensor], 0))
+    heads.iter = 0          # same dropout seeds (unused: dropout 0) and same step counter
+    props = [[item[k].to("cuda")] for k in ("proposals1", "proposals1_flip", "proposals2", "proposals2_flip")]
+    _, direct = heads([im1, im1f, im2, im2f], [f1, f2], props, [[item["instances1"].to("cuda")], None, None, None])
+    for k in losses:
+        assert torch.equal(losses[k], direct[k]), k
+    # inference: one view, post-processed to the dataset's resolution
+    model.eval()
+    test_item = {"image": item["image2"], "height": 120, "width": 160, "proposals": item["proposals2"]}
+    out = model([test_item])[0]["instances"]
+    assert out.image_size == (120, 160) and len(out) <= cfg.TEST.DETECTIONS_PER_IMAGE
+    assert float(out.pred_boxes.tensor[:, 2].max()) <= 160.0 and float(out.pred_boxes.tensor[:, 3].max()) <= 120.0
+    raw, all_scores, all_boxes = model.inference([test_item], do_postprocess=False)
+    assert all_scores[0].shape == (1, R, C + 1) and raw[0].image_size == (144, 192)
+    # the TTA wrapper on top of it (fused and view by view agree on the number of views and produce detections)
+    img8 = (item["image1"]).to(torch.uint8)
+    dd = {"image": img8, "height": 120, "width": 160, "proposals": item["proposals1"]}
+    tta = GeneralizedRCNNWithTTAAVG(cfg, model)
+    inst = tta([dd])[0]["instances"]
+    inst2 = GeneralizedRCNNWithTTAAVG(cfg, model, fuse_views=False)([dd])[0]["instances"]
+    assert len(inst) > 0 and abs(len(inst) - len(inst2)) <= 3
+    assert (inst.scores[:-1] >= inst.scores[1:]).all()

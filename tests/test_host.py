@@ -200,3 +200,25 @@ def test_tta_mapper_host_side_matches_reference_views():
     p = ViewSpec(375, 500, 480, 640, True, orig_hw=(750, 1000)).params(batch_index=1.0)
     assert p == [640 / 500, 480 / 375, 1.0, 640.0, 480.0, 1.0, 500 / 640, 375 / 480, 2.0, 2.0]
     assert len(ViewSpec(10, 10, 20, 20, False).params()) == 10
+
+
+def test_meta_arch_host_helpers():
+    """ImageList.from_tensors and detector_postprocess of the MultiInputRCNN mirror (host logic, no GPU)."""
+    from sos_wsod_b200.modeling import MultiInputRCNN, detector_postprocess
+    from sos_wsod_b200.structures import Boxes, ImageList, Instances
+
+    il = ImageList.from_tensors([torch.zeros(3, 10, 12), torch.ones(3, 8, 15)], 4)
+    assert il.tensor.shape == (2, 3, 12, 16) and il.image_sizes == [(10, 12), (8, 15)]
+    assert float(il.tensor[1, :, :8, :15].min()) == 1.0 and float(il.tensor[1, :, 8:, :].max()) == 0.0
+    one = ImageList.from_tensors([torch.ones(3, 7, 9)])
+    assert one.tensor.shape == (1, 3, 7, 9)
+    r = Instances((10, 20), pred_boxes=Boxes(torch.tensor([[1.0, 2.0, 30.0, 8.0], [5.0, 5.0, 5.0, 9.0]])),
+                  scores=torch.tensor([0.5, 0.4]))
+    o = detector_postprocess(r, 20, 40)
+    assert o.image_size == (20, 40) and o.pred_boxes.tensor.tolist() == [[2.0, 4.0, 40.0, 16.0]] and o.scores.tolist() == [0.5]
+    m = MultiInputRCNN(backbone=torch.nn.Identity(), proposal_generator=None, roi_heads=torch.nn.Identity(),
+                       pixel_mean=(1.0, 2.0, 3.0), pixel_std=(1.0, 1.0, 2.0))
+    imgs = m.preprocess_image_inference([{"image": torch.full((3, 4, 5), 5.0)}])
+    assert imgs.tensor.shape == (1, 3, 4, 5) and imgs.tensor[0, :, 0, 0].tolist() == [4.0, 3.0, 1.0]
+    with pytest.raises(AssertionError, match="imgs_per_gpu=1"):
+        m([{}, {}])
