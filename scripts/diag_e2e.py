@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Diagnostics for the e2e arm of bench.py: pinned H2D bandwidth at the step's input size, and the host time one
 plugin-surface step takes to ISSUE (no synchronisation inside)."""
-import os, sys, time, torch
+import os, sys, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 dev = torch.device("cuda", 0)
 shapes = [(2, 512, 60, 80), (2, 512, 72, 96)]

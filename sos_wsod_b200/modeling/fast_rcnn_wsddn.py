@@ -1,7 +1,6 @@
 """WSDDN predictor (uwsod/projects/WSL/wsl/modeling/roi_heads/fast_rcnn_wsddn.py:154-832, the parts on the OICR+
 path): two Linear streams `cls` / `det` (names and Xavier init :490-498), scores = softmax_c * softmax_r
 (:558-567), image-level BCE (:340-375, :658-681)."""
-from typing import List
 
 import torch
 from torch import nn

@@ -14,7 +14,7 @@ from torch.autograd.function import once_differentiable
 
 from ..engine import HeadConfig, HeadOperands, OICRPlusHeadEngine, ViewBatch
 from ..registry import ROI_HEADS_REGISTRY
-from ..structures import Boxes, ImageList, Instances, ShapeSpec
+from ..structures import Instances, ShapeSpec
 from .box_head import build_box_head
 from .fast_rcnn_oicr import OICROutputLayers, _detections_to_instances
 from .fast_rcnn_wsddn import WSDDNOutputLayers

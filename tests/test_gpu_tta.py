@@ -177,7 +177,7 @@ def test_tta_wrapper_drop_in(ops):
     inference of the per-view head outputs; views that clip a proposal to nothing are handled like the reference."""
     from sos_wsod_b200.config import get_cfg
     from sos_wsod_b200.modeling import build_roi_heads
-    from sos_wsod_b200.modeling.test_time_augmentation_avg import DatasetMapperTTAAVG, GeneralizedRCNNWithTTAAVG
+    from sos_wsod_b200.modeling.test_time_augmentation_avg import GeneralizedRCNNWithTTAAVG
     from sos_wsod_b200.structures import Boxes, Instances, ShapeSpec
 
     torch.manual_seed(2)
