@@ -825,7 +825,7 @@ roi_pool_bwd_q_kernel(const __grid_constant__ CUtensorMap tmap_arg, const __grid
     uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
     float* planes = reinterpret_cast<float*>(gen_base);                          // [CT][plane_stride]
     const uint32_t plane_bytes = (uint32_t)CT * cfg.plane_stride * 4;            // multiple of 128
-    const uint32_t arg_box = (uint32_t)RT * BW * 2;                              // multiples of 128 (RT >= 8)
+    const uint32_t arg_box = (uint32_t)RT * BW * 2;                              // multiples of 128 (checked by the host)
     const uint32_t grad_box = (uint32_t)RT * BW * sizeof(GradT);
     const uint32_t arg_stage = nbox * arg_box, grad_stage = nbox * grad_box;
     const uint32_t ring_off = plane_bytes;
@@ -1141,7 +1141,8 @@ static bool pick_bwd_q_cfg(int n, int c, int h, int w, int grad_bytes, BwdQCfg* 
                     if ((force_p && P != force_p) || (force_lq && LQ != force_lq)) continue;
                     const size_t fixed = (size_t)CT * plane_stride * 4 + (size_t)NP * (1 << LQ) * kBwdQSlotBytes + 128 /*align*/ +
                                          2304 /*barriers, counters, roi meta, dummies*/;
-                    for (int RT = kBwdFastMaxRT; RT >= 8; RT >>= 1) {   // RT * BW * 2 bytes per box: a multiple of 128
+                    for (int RT = kBwdFastMaxRT; RT >= 4; RT >>= 1) {
+                        if (((size_t)RT * BW * 2) % 128 != 0) continue;   // every TMA box starts 128-byte aligned
                         const size_t stage = (size_t)nbox * RT * BW * (2 + grad_bytes);
                         if (fixed + 2 * stage > (size_t)max_smem) continue;
                         int stages = (int)(((size_t)max_smem - fixed) / stage);
