@@ -11,15 +11,21 @@ the SAME un-vendored library operators the reference calls for the arithmetic
 image, so the glue is restated line by line; every function cites the reference
 file:line it follows.  Prefixes: ``W/`` = uwsod/projects/WSL/, ``U/`` = uwsod/.
 
-Parity pin status:
-  * pairwise_iou  -- pinned by the reference KAT U/tests/structures/test_boxes.py:150-173
-  * Matcher       -- pinned by the reference KAT U/tests/modeling/test_matcher.py:19-27
-  * Box2BoxTransform -- pinned by the round-trip property U/tests/modeling/test_box2box_transform.py:16-31
+Parity pin status -- every part is pinned:
+  * pairwise_iou  -- the reference KAT U/tests/structures/test_boxes.py:150-173
+  * Matcher       -- the reference KAT U/tests/modeling/test_matcher.py:19-27
+  * Box2BoxTransform -- the round-trip property U/tests/modeling/test_box2box_transform.py:16-31
   * roi_pool / nms -- are the library ops themselves (torchvision 0.26 CPU kernels), cross-checked
     by the independent scalar C restatement in oracle/ref_kernels.c
-  * WSDDN scores/BCE, pseudo-GT mining, OICR labels/weights/losses, K-branch averaging, TTA merge,
-    VOC writer: PARITY UNPINNED by the reference (it ships no test/fixture for them); the seeded
-    golden vectors in tests/golden/ (made by tests/golden/make_golden.py from this file) are the pin.
+  * pooler, box head, WSDDN scores/BCE, pseudo-GT mining, labelling, OICR losses, K-branch inference:
+    the reference ships no test for them, so tests/golden/make_golden.py imports the REFERENCE'S OWN
+    modules (read-only, through the stub importer tests/golden/ref_import.py) and commits their outputs
+    on seeded inputs (tests/golden/oicr_plus_golden.pt); this file reproduces them bit for bit
+    (tests/test_oracle.py)
+  * TTA view generation + merge: tests/golden/make_golden_tta.py runs the reference's own
+    DatasetMapperTTAAVG / GeneralizedRCNNWithTTAAVG (fvcore's Transform classes restated, the rest
+    from the reference's files) -> tests/golden/tta_golden.pt, reproduced bit for bit
+  * VOC / COCO writers and PGF: oracle/eval_ref.py, pinned the same way (tests/golden/eval_golden.json)
 """
 from __future__ import annotations
 
