@@ -1,5 +1,5 @@
 /*
- * Scalar C restatement of the two third-party operators the reference's hot path leans on
+ * Scalar C restatement of the third-party operators the reference's hot path leans on
  * (un-vendored torchvision: roi_pool and nms).  TEST INFRASTRUCTURE ONLY -- nothing under
  * sos_wsod_b200/ links or loads this file; it is compiled by oracle/Makefile into
  * oracle/_build/libref_kernels.so and loaded with ctypes from tests/ (and bench.py's CPU arm).
@@ -140,4 +140,82 @@ void ref_pairwise_iou(const float* a, int M, const float* b, int R, float* out) 
             float area_b = (q[2] - q[0]) * (q[3] - q[1]);
             out[(size_t)m * R + r] = inter > 0.f ? inter / (area_a + area_b - inter) : 0.f;
         }
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * Test-time augmentation: scalar restatement of
+ *   - transform_proposals (uwsod/projects/WSL/wsl/modeling/test_time_augmentation_avg.py:29-71):
+ *     TransformList([ResizeTransform, HFlipTransform]).apply_box on fp32 boxes -- ResizeTransform.apply_coords
+ *     (uwsod/detectron2/data/transforms/transform.py:123-126) multiplies by the double new_w / w rounded to fp32;
+ *     fvcore Transform.apply_box (un-vendored, published) takes the min / max of the 4 transformed corners after
+ *     every member; HFlipTransform: x -> width - x -- then Boxes.clip and Boxes.nonempty
+ *     (uwsod/detectron2/structures/boxes.py:183-210);
+ *   - the per-view inverse of GeneralizedRCNNWithTTAAVG._get_augmented_boxes (:353-365).
+ * ------------------------------------------------------------------------------------------------ */
+static inline float fminf2(float a, float b) { return a < b ? a : b; }
+static inline float fmaxf2(float a, float b) { return a > b ? a : b; }
+static inline float clampf(float v, float lo, float hi) { return fminf2(fmaxf2(v, lo), hi); }
+
+/* boxes [n,4] in the stored image (h x w) -> out [n,4] in the view (new_h x new_w), keep [n] */
+void ref_tta_transform_proposals(const float* boxes, int n, int h, int w, int new_h, int new_w, int flipped,
+                                 float min_box_size, float* out, uint8_t* keep) {
+    const float sx = (float)((double)new_w * 1.0 / (double)w);
+    const float sy = (float)((double)new_h * 1.0 / (double)h);
+    for (int i = 0; i < n; ++i) {
+        const float* b = boxes + 4 * i;
+        float xa = b[0] * sx, xb = b[2] * sx, ya = b[1] * sy, yb = b[3] * sy;
+        float x1 = fminf2(xa, xb), x2 = fmaxf2(xa, xb), y1 = fminf2(ya, yb), y2 = fmaxf2(ya, yb);
+        if (flipped) {
+            xa = (float)new_w - x1;
+            xb = (float)new_w - x2;
+            x1 = fminf2(xa, xb);
+            x2 = fmaxf2(xa, xb);
+        }
+        x1 = clampf(x1, 0.f, (float)new_w);
+        x2 = clampf(x2, 0.f, (float)new_w);
+        y1 = clampf(y1, 0.f, (float)new_h);
+        y2 = clampf(y2, 0.f, (float)new_h);
+        out[4 * i + 0] = x1;
+        out[4 * i + 1] = y1;
+        out[4 * i + 2] = x2;
+        out[4 * i + 3] = y2;
+        keep[i] = ((x2 - x1) > min_box_size) && ((y2 - y1) > min_box_size);
+    }
+}
+
+/* boxes [n,4] in the view -> out [n,4] in the stored image; post_w / post_h > 0: then on to the dataset's size
+ * (the reference's pre-transform, :169-173), else pass 0 */
+void ref_tta_inverse_boxes(const float* boxes, int n, int h, int w, int new_h, int new_w, int flipped, int post_h,
+                           int post_w, float* out) {
+    const float sx = (float)((double)w * 1.0 / (double)new_w);
+    const float sy = (float)((double)h * 1.0 / (double)new_h);
+    for (int i = 0; i < n; ++i) {
+        const float* b = boxes + 4 * i;
+        float x1 = b[0], y1 = b[1], x2 = b[2], y2 = b[3];
+        if (flipped) {
+            const float xa = (float)new_w - x1, xb = (float)new_w - x2;
+            x1 = fminf2(xa, xb);
+            x2 = fmaxf2(xa, xb);
+        }
+        float xa = x1 * sx, xb = x2 * sx, ya = y1 * sy, yb = y2 * sy;
+        x1 = fminf2(xa, xb);
+        x2 = fmaxf2(xa, xb);
+        y1 = fminf2(ya, yb);
+        y2 = fmaxf2(ya, yb);
+        if (post_w > 0 && post_h > 0) {
+            const float px = (float)((double)post_w * 1.0 / (double)w), py = (float)((double)post_h * 1.0 / (double)h);
+            xa = x1 * px;
+            xb = x2 * px;
+            ya = y1 * py;
+            yb = y2 * py;
+            x1 = fminf2(xa, xb);
+            x2 = fmaxf2(xa, xb);
+            y1 = fminf2(ya, yb);
+            y2 = fmaxf2(ya, yb);
+        }
+        out[4 * i + 0] = x1;
+        out[4 * i + 1] = y1;
+        out[4 * i + 2] = x2;
+        out[4 * i + 3] = y2;
+    }
 }

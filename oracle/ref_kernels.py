@@ -72,3 +72,24 @@ def pairwise_iou(a: np.ndarray, b: np.ndarray) -> np.ndarray:
     lib().ref_pairwise_iou(_p(a, ctypes.c_float), a.shape[0], _p(b, ctypes.c_float), b.shape[0],
                            _p(out, ctypes.c_float))
     return out
+
+
+def tta_transform_proposals(boxes: np.ndarray, hw, new_hw, flipped: bool, min_box_size: float = 0.0):
+    boxes = np.ascontiguousarray(boxes, dtype=np.float32)
+    n = boxes.shape[0]
+    out = np.empty((n, 4), np.float32)
+    keep = np.empty((n,), np.uint8)
+    lib().ref_tta_transform_proposals(_p(boxes, ctypes.c_float), n, int(hw[0]), int(hw[1]), int(new_hw[0]), int(new_hw[1]),
+                                      int(flipped), ctypes.c_float(min_box_size), _p(out, ctypes.c_float),
+                                      _p(keep, ctypes.c_uint8))
+    return out, keep.astype(bool)
+
+
+def tta_inverse_boxes(boxes: np.ndarray, hw, new_hw, flipped: bool, post_hw=None) -> np.ndarray:
+    boxes = np.ascontiguousarray(boxes, dtype=np.float32)
+    n = boxes.shape[0]
+    out = np.empty((n, 4), np.float32)
+    ph, pw = (int(post_hw[0]), int(post_hw[1])) if post_hw is not None else (0, 0)
+    lib().ref_tta_inverse_boxes(_p(boxes, ctypes.c_float), n, int(hw[0]), int(hw[1]), int(new_hw[0]), int(new_hw[1]),
+                                int(flipped), ph, pw, _p(out, ctypes.c_float))
+    return out

@@ -245,3 +245,28 @@ def test_tta_transform_edge_cases():
     assert keep.tolist() == [True, False, False]
     out2, keep2 = ref.tta_transform_proposals(b[:1], (60, 80), (120, 160), False, min_box_size=40.0)
     assert keep2.tolist() == [False] and torch.equal(out2[0], torch.tensor([20.0, 20.0, 60.0, 80.0]))
+
+
+def test_tta_scalar_c_restatement_matches_reference_fixtures(tta_gold):
+    """oracle/ref_kernels.c (independent scalar restatement) against the reference-generated TTA fixtures and the
+    torch oracle: transformed proposals bit for bit; inverse transforms bit for bit (so the mean over views is too)."""
+    for c in tta_gold["cases"]:
+        h, w = c["stored_hw"]
+        C = c["C"]
+        sizes = ref.tta_view_sizes(h, w, c["min_sizes"], c["max_size"], c["flip"])
+        boxes = c["boxes"][: c["topk"]]
+        post = None if c["stored_hw"] == c["dataset_hw"] else c["dataset_hw"]
+        inv = []
+        for i, ((nh, nw, fl), v) in enumerate(zip(sizes, c["views"])):
+            out, keep = ref_kernels.tta_transform_proposals(boxes.numpy(), (h, w), (nh, nw), fl)
+            assert keep.all() and np.array_equal(out, v["proposal_boxes"].numpy()), (c["name"], i)
+            b = ref_kernels.tta_inverse_boxes(c["view_boxes"][i].reshape(-1, 4).numpy(), (h, w), (nh, nw), fl, post)
+            e = ref.tta_inverse_boxes(c["view_boxes"][i].reshape(-1, 4), w * 1.0 / nw, h * 1.0 / nh, fl, nw, _tta_post(c))
+            assert np.array_equal(b, e.numpy()), (c["name"], i)
+            inv.append(torch.from_numpy(b).reshape(-1, 4 * C))
+        assert torch.equal(torch.stack(inv).mean(0), c["merged_boxes"]), c["name"]
+    # edge cases: malformed, outside, degenerate, min size
+    b = np.array([[30.0, 10.0, 10.0, 40.0], [-50.0, -50.0, -10.0, -5.0], [5.0, 5.0, 5.0, 30.0]], np.float32)
+    out, keep = ref_kernels.tta_transform_proposals(b, (60, 80), (120, 160), True)
+    eo, ek = ref.tta_transform_proposals(torch.from_numpy(b), (60, 80), (120, 160), True)
+    assert np.array_equal(out, eo.numpy()) and keep.tolist() == ek.tolist() == [True, False, False]
