@@ -205,7 +205,8 @@ def run_reference_arm(args):
     # bounded sample: the whole --steps K --warmup W run stays within ~2-3 minutes of host work, one step at most the
     # full 2000-proposal workload (~7 s on 16 cores)
     n_warm = max(1, min(args.warmup, 2))
-    views, gt, params, r, gflops = cpu_sample_setup(min(6.0, 100.0 / (args.steps + n_warm)))
+    budget = float(os.environ.get("SOSWSOD_REF_BUDGET_SECONDS", "100"))
+    views, gt, params, r, gflops = cpu_sample_setup(min(6.0, budget / (args.steps + n_warm)))
     for _ in range(n_warm):
         cpu_reference_step(views, gt, params)
     t0 = time.perf_counter()

@@ -222,3 +222,25 @@ def test_meta_arch_host_helpers():
     assert imgs.tensor.shape == (1, 3, 4, 5) and imgs.tensor[0, :, 0, 0].tolist() == [4.0, 3.0, 1.0]
     with pytest.raises(AssertionError, match="imgs_per_gpu=1"):
         m([{}, {}])
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the reference's CPU path on the host cores): one JSON line with the keys the
+    driver reads; under torchrun only rank 0 works (the other ranks exit 0 without output)."""
+    import json
+
+    env = dict(os.environ, SOSWSOD_REF_BUDGET_SECONDS="1.5")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "1"],
+                       capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    b = json.loads(lines[0])
+    assert b["impl"] == "reference" and b["unit"] == "image-views/s" and b["higher_is_better"] is True
+    assert b["metric"] == "OICR+ head fwd+bwd images/s" and b["steps"] == 2 and b["value"] > 0
+    assert b["cpu_baseline"]["kind"] == "port" and b["cpu_baseline"]["cores"] >= 1 and b["cpu_baseline"]["value"] == b["value"]
+    assert b["e2e"] == {"value": b["value"], "unit": b["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in b["config"] and "sample" in b["config"]
+    r1 = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "2"],
+                        capture_output=True, text=True, env=dict(env, RANK="1", WORLD_SIZE="2"), timeout=120)
+    assert r1.returncode == 0 and r1.stdout.strip() == ""
