@@ -58,5 +58,8 @@ def get_cfg() -> CfgNode:
     cfg.MODEL.LOAD_PROPOSALS = True
     cfg.MODEL.MASK_ON = False
     cfg.MODEL.KEYPOINT_ON = False
-    cfg.SOLVER = C(AMP=C(ENABLED=False))
+    # voc07_oicr_plus.yaml:36-45 + detectron2/config/defaults.py:509-547,655-656
+    cfg.SOLVER = C(AMP=C(ENABLED=False), BASE_LR=0.001, MOMENTUM=0.9, NESTEROV=False, WEIGHT_DECAY=0.0005,
+                   WEIGHT_DECAY_NORM=0.0, BIAS_LR_FACTOR=2.0, WEIGHT_DECAY_BIAS=0.0, REFINE_SCALE_ON=False,
+                   REFINE_LR_SCALE=1.0, CLIP_GRADIENTS=C(ENABLED=False))
     return cfg

@@ -446,3 +446,44 @@ def test_multi_input_rcnn_mirror(cuda_lib):
     inst2 = GeneralizedRCNNWithTTAAVG(cfg, model, fuse_views=False)([dd])[0]["instances"]
     assert len(inst) > 0 and abs(len(inst) - len(inst2)) <= 3
     assert (inst.scores[:-1] >= inst.scores[1:]).all()
+
+
+def test_b200_sgd_matches_torch_sgd_and_refreshes_operands(cuda_lib):
+    """solver.B200SGD (one fused pass per parameter) == torch.optim.SGD with the same per-parameter groups; a step bumps
+    the parameters' version counters, so the head re-casts its bf16 GEMM operands on the next forward."""
+    import copy
+
+    from sos_wsod_b200.solver import B200SGD
+
+    torch.manual_seed(0)
+    m1 = torch.nn.Sequential(torch.nn.Linear(37, 19), torch.nn.Tanh(), torch.nn.Linear(19, 5)).cuda()
+    m2 = copy.deepcopy(m1)
+
+    def groups(m):
+        return [{"params": [p], "lr": 2e-3 if n.endswith("bias") else 1e-3, "weight_decay": 0.0 if n.endswith("bias") else 5e-4}
+                for n, p in m.named_parameters()]
+
+    o1, o2 = B200SGD(groups(m1), 1e-3, momentum=0.9), torch.optim.SGD(groups(m2), 1e-3, momentum=0.9)
+    x = torch.randn(11, 37, device="cuda")
+    v0 = [p._version for p in m1.parameters()]
+    for _ in range(4):
+        for m, o in ((m1, o1), (m2, o2)):
+            o.zero_grad()
+            m(x).square().mean().backward()
+            o.step()
+    for p1, p2 in zip(m1.parameters(), m2.parameters()):
+        torch.testing.assert_close(p1, p2, rtol=1e-5, atol=1e-7)
+    assert all(p._version > v for p, v in zip(m1.parameters(), v0))
+    assert all("momentum_buffer" in o1.state[p] for p in m1.parameters())
+    # through the head: operands follow the masters after a step
+    eng, vb, views, p, gt_classes, cfg = _small_setup(R=120, seed=5)
+    masters = [t.requires_grad_(True) for t in eng.op.master.values()]
+    out = eng.train_step(vb, torch.unique(gt_classes).cuda())
+    for t, k in zip(masters, eng.op.master.keys()):
+        t.grad = out.grads[k].clone()
+    w7_before = eng.op.w7.clone()
+    opt = B200SGD([{"params": masters}], 1e-2, momentum=0.9, weight_decay=5e-4)
+    opt.step()
+    eng.train_step(vb, torch.unique(gt_classes).cuda())
+    assert not torch.equal(eng.op.w7, w7_before)
+    assert torch.equal(eng.op.w7, eng.op.master["fc2_w"].detach().to(torch.bfloat16))

@@ -244,3 +244,44 @@ def test_bench_reference_arm_prints_the_contract_line():
     r1 = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "2"],
                         capture_output=True, text=True, env=dict(env, RANK="1", WORLD_SIZE="2"), timeout=120)
     assert r1.returncode == 0 and r1.stdout.strip() == ""
+
+
+def test_solver_param_groups_follow_the_reference_rules():
+    """get_optimizer_param_groups (uwsod/detectron2/solver/build.py:143-218): bias lr x BIAS_LR_FACTOR with
+    WEIGHT_DECAY_BIAS, norm layers WEIGHT_DECAY_NORM; with REFINE_SCALE_ON the name-keyed rules and REFINE_LR_SCALE."""
+    from sos_wsod_b200.config import get_cfg
+    from sos_wsod_b200.modeling import build_roi_heads
+    from sos_wsod_b200.solver import B200SGD, build_optimizer, get_optimizer_param_groups
+    from sos_wsod_b200.structures import ShapeSpec
+
+    cfg = get_cfg()
+    cfg.MODEL.ROI_BOX_HEAD.DAN_DIM = [64, 64]
+    heads = build_roi_heads(cfg, {"plain5": ShapeSpec(channels=4, stride=8)})
+    model = torch.nn.Sequential()
+    model.add_module("backbone", torch.nn.Sequential(torch.nn.Conv2d(3, 4, 3), torch.nn.BatchNorm2d(4)))
+    model.add_module("roi_heads", heads)
+    names = {id(p): n for n, p in model.named_parameters()}
+    groups = get_optimizer_param_groups(cfg, model)
+    assert len(groups) == len(names)
+    got = {names[id(g["params"][0])]: (g["lr"], g["weight_decay"]) for g in groups}
+    for n, (lr, wd) in got.items():
+        if n.startswith("backbone.1."):
+            assert (lr, wd) == ((0.002 if n.endswith("bias") else 0.001), 0.0) or (lr, wd) == (0.001, 0.0), n   # norm layer
+        elif n.endswith("bias"):
+            assert (lr, wd) == (0.002, 0.0), n
+        else:
+            assert (lr, wd) == (0.001, 0.0005), n
+    assert got["backbone.1.weight"] == (0.001, 0.0) and got["backbone.1.bias"] == (0.001, 0.0)
+    cfg.SOLVER.REFINE_SCALE_ON, cfg.SOLVER.REFINE_LR_SCALE = True, 3.0
+    got = {names[id(g["params"][0])]: (g["lr"], g["weight_decay"]) for g in get_optimizer_param_groups(cfg, model)}
+    assert got["roi_heads.box_refinery_0.cls_score.bias"] == (0.001 * 2.0 * 3.0, 0.0)
+    assert got["roi_heads.box_refinery_2.bbox_pred.weight"] == (0.001 * 3.0, 0.0005)
+    assert got["roi_heads.box_head.fc1.bias"] == (0.002, 0.0) and got["roi_heads.box_predictor.cls.weight"] == (0.001, 0.0005)
+    opt = build_optimizer(cfg, model)
+    assert isinstance(opt, B200SGD) and opt.defaults["momentum"] == 0.9 and len(opt.param_groups) == len(names)
+    model.backbone[0].weight.grad = torch.zeros_like(model.backbone[0].weight)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        opt.step()
+    cfg.SOLVER.NESTEROV = True
+    with pytest.raises(NotImplementedError):
+        build_optimizer(cfg, model)
