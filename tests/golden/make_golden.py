@@ -152,8 +152,9 @@ def main():
     out["infer"] = {"all_scores": all_scores[0].detach(), "all_boxes": all_boxes[0].detach(),
                     "pred_boxes": inst[0].pred_boxes.tensor.detach(), "scores": inst[0].scores.detach(),
                     "pred_classes": inst[0].pred_classes, "pred_inds": inds[0]}
-    torch.save(out, os.path.join(HERE, "oicr_plus_golden.pt"))
-    sz = os.path.getsize(os.path.join(HERE, "oicr_plus_golden.pt"))
+    dst = os.path.join(os.environ.get("SOSWSOD_GOLDEN_OUT", HERE), "oicr_plus_golden.pt")
+    torch.save(out, dst)
+    sz = os.path.getsize(dst)
     print("wrote oicr_plus_golden.pt", sz, "bytes;", {k: (len(v) if hasattr(v, "__len__") else "") for k, v in out.items()})
 
 

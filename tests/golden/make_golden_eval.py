@@ -126,7 +126,7 @@ def main():
     gold["contain"] = [{"a": a, "b": b, "val": ref_pgf.contain_cal(a, b)} for a, b in
                        [([10.0, 10.0, 20.0, 20.0], [5.0, 5.0, 40.0, 40.0]), ([0.0, 0.0, 10.0, 10.0], [5.0, 5.0, 10.0, 10.0]),
                         ([3.5, 2.25, 0.0, 7.0], [0.0, 0.0, 50.0, 50.0]), ([100.0, 100.0, 5.0, 5.0], [0.0, 0.0, 50.0, 50.0])]]
-    path = os.path.join(HERE, "eval_golden.json")
+    path = os.path.join(os.environ.get("SOSWSOD_GOLDEN_OUT", HERE), "eval_golden.json")
     with open(path, "w") as f:
         json.dump(gold, f)
     n_after = [sum(len(v) for v in c["after_pgf"].values()) for c in cases]

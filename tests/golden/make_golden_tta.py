@@ -107,7 +107,7 @@ def main():
         run_case("stored_not_dataset_size", g, (48, 64), (96, 128), (48, 72), 4000, True, 180, 8, 4000),
         run_case("coco_width_16views", g, (52, 70), (52, 70), (48, 57, 67, 76, 86, 96, 105, 115), 4000, True, 40, 80, 4000),
     ]
-    path = os.path.join(HERE, "tta_golden.pt")
+    path = os.path.join(os.environ.get("SOSWSOD_GOLDEN_OUT", HERE), "tta_golden.pt")
     torch.save({"cases": cases, "numpy": np.__version__, "torch": str(torch.__version__)}, path)
     for c in cases:
         print(c["name"], "views", len(c["views"]), "R", len(c["views"][0]["proposal_boxes"]), "dets", len(c["det_scores"]),
