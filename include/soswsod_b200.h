@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define SOSWSOD_ABI_VERSION 6
+#define SOSWSOD_ABI_VERSION 7
 
 #define SOSWSOD_OK 0
 #define SOSWSOD_ERR_INVALID (-1)     /* bad shape / null pointer / misalignment */
@@ -299,6 +299,25 @@ int soswsod_detect(const float* probs, const float* pred_boxes, int R, int C, fl
  * and, if param_bf16 != NULL, the refreshed bf16 GEMM-operand copy of p in the same pass. Contiguous fp32. */
 int soswsod_sgd_step(float* param, const float* grad, float* momentum_buf, long long n, float lr, float momentum,
                      float weight_decay, float grad_scale, void* param_bf16, soswsod_stream_t stream);
+
+/* The same update for up to SOSWSOD_SGD_MAX_TENSORS tensors (or shards: pass pre-offset pointers) in ONE launch --
+ * the whole `optimizer.step()` of uwsod/projects/WSL/tools/train_net_multi.py:157-164 for the head's 8 + 4K
+ * parameters.  `tensors` is a HOST array (copied into the launch parameters).  Per tensor: lr / weight_decay of its
+ * parameter group; out_bf16 (may be NULL) receives the refreshed bf16 GEMM operand, out_f32 (may be NULL) an fp32
+ * copy of the new value (the fused head-bias vector). */
+#define SOSWSOD_SGD_MAX_TENSORS 32
+typedef struct soswsod_sgd_tensor {
+    float* param;
+    const float* grad;
+    float* momentum_buf;
+    void* out_bf16;
+    float* out_f32;
+    long long n;
+    float lr;
+    float weight_decay;
+} soswsod_sgd_tensor;
+int soswsod_sgd_multi(const soswsod_sgd_tensor* tensors, int count, float momentum, float grad_scale,
+                      soswsod_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * (6) PGF, the consumer of the detection-results json.  Replaces the per-image

@@ -22,6 +22,12 @@ Parity pin status -- every part is pinned:
     modules (read-only, through the stub importer tests/golden/ref_import.py) and commits their outputs
     on seeded inputs (tests/golden/oicr_plus_golden.pt); this file reproduces them bit for bit
     (tests/test_oracle.py)
+  * the WHOLE training step (`train_step`): tests/golden/make_golden_step.py constructs the reference's own
+    OICRPlusHeads and runs its `forward` (get_image_level_gt -> feature split -> `_forward_box`,
+    roi_heads_oicrplus.py:149-430) + backward on seeded inputs, with dropout off and with the reference's own
+    dropout keep-masks recorded -> tests/golden/step_golden.pt; `train_step` reproduces the losses to 1e-6 and every
+    parameter / conv5 gradient to 1e-4 relative (VOC K=3 and COCO K=4 shapes), which pins the view averaging
+    (:290-294, :390-395), the /4 combines (:288, :384-388) and the `2_flip` quirk (:381) by RUNNING them
   * TTA view generation + merge: tests/golden/make_golden_tta.py runs the reference's own
     DatasetMapperTTAAVG / GeneralizedRCNNWithTTAAVG (fvcore's Transform classes restated, the rest
     from the reference's files) -> tests/golden/tta_golden.pt, reproduced bit for bit
@@ -415,6 +421,19 @@ def oicr_accuracy_counters(logits: torch.Tensor, gt_classes: torch.Tensor):
     fg = (gt_classes >= 0) & (gt_classes < bg)
     return (gt_classes.numel(), int(fg.sum()), int((pred == gt_classes).sum()),
             int((pred[fg] == gt_classes[fg]).sum()), int((pred[fg] == bg).sum()))
+
+
+def reference_accuracy_scalars(logits: torch.Tensor, gt_classes: torch.Tensor, num_classes: int):
+    """The EventStorage scalars of fast_rcnn_oicr.py:228-256 (`fast_rcnn/cls_accuracy_r{k}`, `fg_cls_accuracy`,
+    `false_negative`) from the counters above; the fg ratios are absent when there is no foreground row."""
+    n, n_fg, acc, fg_acc, fn = oicr_accuracy_counters(logits, gt_classes)
+    out = {}
+    if n > 0:
+        out["cls_accuracy"] = acc / n
+        if n_fg > 0:
+            out["fg_cls_accuracy"] = fg_acc / n_fg
+            out["false_negative"] = fn / n_fg
+    return out
 
 
 # ----------------------------------------------------------------------------------------------

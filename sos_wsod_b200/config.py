@@ -1,7 +1,7 @@
 """yacs-style config shim (yacs is not installed here) carrying exactly the keys the OICR+ head reads
 (SURVEY.md §5 "Config / flags"), with the values of the released configs
-uwsod/projects/WSL/configs/Detection/code_release/voc07_oicr_plus.yaml + Base-RCNN-DilatedC5.yaml and the
-defaults of uwsod/projects/WSL/wsl/config/defaults.py.  A real detectron2 CfgNode works in its place."""
+uwsod/projects/WSL/configs/Detection/code_release/voc07_oicr_plus.yaml (REFINE_NUM: 4, :56-58) +
+Base-RCNN-DilatedC5.yaml and the defaults of uwsod/projects/WSL/wsl/config/defaults.py.  A real detectron2 CfgNode works in its place."""
 from __future__ import annotations
 
 
@@ -47,7 +47,7 @@ def get_cfg() -> CfgNode:
         NAME="DiscriminativeAdaptionNeck", POOLER_TYPE="ROIPool", POOLER_RESOLUTION=7, POOLER_SAMPLING_RATIO=0,
         DAN_DIM=[4096, 4096], BBOX_REG_WEIGHTS=(10.0, 10.0, 5.0, 5.0), SMOOTH_L1_BETA=0.0,
         BBOX_REG_LOSS_TYPE="smooth_l1", BBOX_REG_LOSS_WEIGHT=1.0, CLS_AGNOSTIC_BBOX_REG=False, DROPOUT=0.5)
-    cfg.WSL = C(REFINE_NUM=3, REFINE_REG=[True, True, True, True], REFINE_MIST=True, MIST_P=0.10, MIST_THRE=0.05,
+    cfg.WSL = C(REFINE_NUM=4, REFINE_REG=[True, True, True, True], REFINE_MIST=True, MIST_P=0.10, MIST_THRE=0.05,
                 MIST_TYPE="nms", MEAN_LOSS=True)
     cfg.OICRPLUS = C(BBOX_UPDATE=False, PROPOSAL_NUM=2000)
     # detection_result_test.yaml:46-50 (shipped with ENABLED: False), Base-RCNN-DilatedC5.yaml:4-10

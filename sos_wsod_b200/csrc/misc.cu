@@ -156,9 +156,108 @@ __global__ void sgd_step_kernel(float* __restrict__ p, const float* __restrict__
     if (p_bf16) p_bf16[i] = __float2bfloat16_rn(np);
 }
 
+// The same update for up to SOSWSOD_SGD_MAX_TENSORS parameter tensors (or shards of them) in ONE launch: the table of
+// tensors travels in the kernel parameters, a block owns 4096 consecutive elements of one tensor, 128-bit accesses
+// where the tensor's pointers allow.  Sinks: the bf16 GEMM-operand copy and / or an fp32 copy of the new value.
+constexpr int kSgdBlockElems = 4096;
+
+struct SgdBatch {
+    soswsod_sgd_tensor t[SOSWSOD_SGD_MAX_TENSORS];
+    int block_start[SOSWSOD_SGD_MAX_TENSORS + 1];
+    int count;
+    float momentum, gscale;
+};
+
+__global__ void __launch_bounds__(256)
+sgd_multi_kernel(const __grid_constant__ SgdBatch b) {
+    int ti = 0;
+    while (ti + 1 < b.count && (int)blockIdx.x >= b.block_start[ti + 1]) ++ti;
+    const soswsod_sgd_tensor& t = b.t[ti];
+    const long long e0 = (long long)((int)blockIdx.x - b.block_start[ti]) * kSgdBlockElems;
+    const long long e1 = e0 + kSgdBlockElems < t.n ? e0 + kSgdBlockElems : t.n;
+    float* __restrict__ p = t.param;
+    const float* __restrict__ g = t.grad;
+    float* __restrict__ mb = t.momentum_buf;
+    __nv_bfloat16* __restrict__ ob = reinterpret_cast<__nv_bfloat16*>(t.out_bf16);
+    float* __restrict__ of = t.out_f32;
+    const float lr = t.lr, wd = t.weight_decay, mom = b.momentum, gs = b.gscale;
+    const bool vec = ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(mb) |
+                       reinterpret_cast<uintptr_t>(of)) & 15) == 0 && (reinterpret_cast<uintptr_t>(ob) & 7) == 0;
+    auto upd = [&](float pv, float gv, float bv, float& nb) {
+        nb = mom * bv + (gv * gs + wd * pv);
+        return pv - lr * nb;
+    };
+    long long i = e0 + 4LL * threadIdx.x;
+    if (vec) {
+        for (; i + 4 <= e1; i += 4 * 256) {
+            const float4 pv = *reinterpret_cast<const float4*>(p + i);
+            const float4 gv = __ldcs(reinterpret_cast<const float4*>(g + i));      // the gradient is read once
+            const float4 bv = *reinterpret_cast<const float4*>(mb + i);
+            float4 nb, np;
+            np.x = upd(pv.x, gv.x, bv.x, nb.x);
+            np.y = upd(pv.y, gv.y, bv.y, nb.y);
+            np.z = upd(pv.z, gv.z, bv.z, nb.z);
+            np.w = upd(pv.w, gv.w, bv.w, nb.w);
+            *reinterpret_cast<float4*>(mb + i) = nb;
+            *reinterpret_cast<float4*>(p + i) = np;
+            if (ob) {
+                const __nv_bfloat162 lo = __floats2bfloat162_rn(np.x, np.y), hi = __floats2bfloat162_rn(np.z, np.w);
+                uint2 u;
+                u.x = *reinterpret_cast<const uint32_t*>(&lo);
+                u.y = *reinterpret_cast<const uint32_t*>(&hi);
+                *reinterpret_cast<uint2*>(ob + i) = u;
+            }
+            if (of) *reinterpret_cast<float4*>(of + i) = np;
+        }
+        // tail (n % 4) of the tensor: the lanes past the last full vector
+        if (i < e1 && i + 4 > e1) {
+            for (long long j = i; j < e1; ++j) {
+                float nb;
+                const float np = upd(p[j], g[j], mb[j], nb);
+                mb[j] = nb;
+                p[j] = np;
+                if (ob) ob[j] = __float2bfloat16_rn(np);
+                if (of) of[j] = np;
+            }
+        }
+    } else {
+        for (long long j = e0 + threadIdx.x; j < e1; j += 256) {
+            float nb;
+            const float np = upd(p[j], g[j], mb[j], nb);
+            mb[j] = nb;
+            p[j] = np;
+            if (ob) ob[j] = __float2bfloat16_rn(np);
+            if (of) of[j] = np;
+        }
+    }
+}
+
 }  // namespace soswsod
 
 using namespace soswsod;
+
+extern "C" int soswsod_sgd_multi(const soswsod_sgd_tensor* tensors, int count, float momentum, float grad_scale,
+                                 soswsod_stream_t stream) {
+    SOSWSOD_CHECK_ARG(tensors && count > 0 && count <= SOSWSOD_SGD_MAX_TENSORS, "sgd_multi: 1..%d tensors per call",
+                      SOSWSOD_SGD_MAX_TENSORS);
+    SgdBatch b;
+    b.count = count;
+    b.momentum = momentum;
+    b.gscale = grad_scale;
+    long long blocks = 0;
+    for (int i = 0; i < count; ++i) {
+        SOSWSOD_CHECK_ARG(tensors[i].param && tensors[i].grad && tensors[i].momentum_buf && tensors[i].n > 0,
+                          "sgd_multi: tensor %d: null pointer or empty", i);
+        b.t[i] = tensors[i];
+        b.block_start[i] = (int)blocks;
+        blocks += (tensors[i].n + kSgdBlockElems - 1) / kSgdBlockElems;
+        SOSWSOD_CHECK_ARG(blocks < (1LL << 30), "sgd_multi: too many elements for one launch");
+    }
+    b.block_start[count] = (int)blocks;
+    sgd_multi_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(b);
+    SOSWSOD_CHECK_LAUNCH();
+    return SOSWSOD_OK;
+}
 
 extern "C" int soswsod_sgd_step(float* param, const float* grad, float* momentum_buf, long long n, float lr,
                                 float momentum, float weight_decay, float grad_scale, void* param_bf16,

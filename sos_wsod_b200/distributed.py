@@ -1,0 +1,167 @@
+"""Data-parallel exchange of the head's parameter gradients (one image per GPU, one exchange per step;
+the reference wraps the model in DistributedDataParallel, uwsod/projects/WSL/tools/train_net_multi.py:75-78, which
+all-reduces 483.8 MB of fp32 gradients per rank and step and then runs the full optimizer on every rank).
+
+Two modes behind one object, both giving every rank the SAME fp32 result as DDP's average:
+
+  "allreduce"  what DDP does: an averaging all-reduce per gradient, started from the engine's gradient hook as soon as
+               the producing kernel is queued.
+  "sharded"    for the two big matrices (fc1.weight 411 MB, fc2.weight 67 MB = 99 % of the bytes): REDUCE-SCATTER the
+               fp32 gradient (rank r receives the averaged rows it owns, in place), update only those rows of the fp32
+               master / momentum with the fused SGD pass -- which writes the rows of the bf16 GEMM operand -- and
+               ALL-GATHER the bf16 operand rows.  Bytes on the wire per rank: (n-1)/n x (484 + 242) MB instead of
+               2 (n-1)/n x 484 MB, optimizer work 1/n, and the all-gather runs behind the next step's ROI pooling
+               (the engine waits for it right before the first GEMM, engine.operand_gate).  The fp32 masters of rows a
+               rank does not own are refreshed on demand (`sync_master()`: state_dict / checkpoint time); the forward
+               and backward only ever read the bf16 operands.  Small tensors (biases, the fused head block) are
+               all-reduced.
+
+Every collective is issued with async_op=True from the stream that produced its input; `Work.wait()` orders the
+consumer's stream behind it -- no host synchronisation anywhere.  Backends without reduce_scatter_tensor / AVG (gloo,
+used by the CPU tests of this host logic) take an all-reduce based path with the same result."""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+class GradientExchange:
+    SHARDED_KEYS = ("fc1_w", "fc2_w")
+
+    def __init__(self, master: Dict[str, torch.Tensor], group=None, mode: str = "sharded", min_shard_elems: int = 1 << 20):
+        """master: HeadOperands.master (key -> fp32 parameter).  mode: "sharded" | "allreduce"."""
+        if not dist.is_initialized():
+            raise RuntimeError("GradientExchange needs an initialised torch.distributed process group")
+        assert mode in ("sharded", "allreduce")
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.mode = mode
+        self.backend = dist.get_backend(group)
+        self.native = self.backend == "nccl"
+        self.master = master
+        self.sharded = set()
+        if mode == "sharded" and self.world > 1:
+            for k in self.SHARDED_KEYS:
+                t = master[k]
+                if t.numel() >= min_shard_elems and t.size(0) % self.world == 0:
+                    self.sharded.add(k)
+        self._works: List = []                         # all-reduces of this step
+        self._rs: List[Tuple[str, torch.Tensor, int, object]] = []     # (key, panel, row0, work) reduce-scatters of this step
+        self._gather: List = []                        # operand all-gathers still in flight
+        self.master_stale = False
+        self._layout: Dict[str, List[Tuple[int, int]]] = {}
+        self.bytes_last_step = {"reduce_scatter": 0, "all_reduce": 0, "all_gather": 0}
+
+    # ------------------------------------------------------------------ gradient side
+    def begin_step(self) -> None:
+        """Start of a training step: nothing of a previous step may be left pending (a step whose gradients were never
+        consumed by an optimizer is dropped after ordering the stream behind its collectives)."""
+        self.wait_gradients()
+        self._rs.clear()
+        self.bytes_last_step = {"reduce_scatter": 0, "all_reduce": 0, "all_gather": 0}
+
+    def hook(self, key: str, grad: torch.Tensor, row0: int) -> None:
+        """The engine's grad_hook: starts the collective of one gradient (or one row panel of fc1.weight)."""
+        if self.world == 1:
+            return
+        if key in self.sharded:
+            rows = grad.size(0)
+            if rows % self.world != 0:
+                raise RuntimeError(f"GradientExchange: a {rows}-row panel of {key} does not split over {self.world} ranks")
+            self.bytes_last_step["reduce_scatter"] += grad.numel() * 4
+            if self.native:
+                mine = grad.chunk(self.world, 0)[self.rank]
+                w = dist.reduce_scatter_tensor(mine, grad, op=dist.ReduceOp.AVG, group=self.group, async_op=True)   # in place
+            else:
+                grad.div_(self.world)
+                w = dist.all_reduce(grad, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+            self._rs.append((key, grad, row0, w))
+        else:
+            self.bytes_last_step["all_reduce"] += grad.numel() * 4
+            if self.native:
+                w = dist.all_reduce(grad, op=dist.ReduceOp.AVG, group=self.group, async_op=True)
+            else:
+                grad.div_(self.world)
+                w = dist.all_reduce(grad, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+            self._works.append(w)
+
+    def wait_gradients(self) -> None:
+        """Orders the current stream behind every gradient collective of this step."""
+        for w in self._works:
+            w.wait()
+        self._works.clear()
+        for _, _, _, w in self._rs:
+            w.wait()
+
+    def owned_rows(self, key: str) -> List[Tuple[int, int]]:
+        """Row ranges [lo, hi) of parameter `key` this rank updates (after wait_gradients): one per exchanged panel for
+        a sharded tensor -- the averaged gradient of exactly those rows sits in the gradient tensor -- else all rows."""
+        if key not in self.sharded:
+            return [(0, self.master[key].size(0))]
+        out = []
+        for k, panel, row0, _ in self._rs:
+            if k == key:
+                per = panel.size(0) // self.world
+                out.append((row0 + self.rank * per, row0 + (self.rank + 1) * per))
+        return out
+
+    # ------------------------------------------------------------------ operand side
+    def gather_operands(self, operands: Dict[str, torch.Tensor]) -> None:
+        """After the sharded update: all-gather the bf16 operand rows (in place) of every panel exchanged this step.
+        operands: key -> bf16 [rows, cols] GEMM operand of master[key]."""
+        for key, panel, row0, _ in self._rs:
+            opnd = operands[key][row0:row0 + panel.size(0)]
+            self.bytes_last_step["all_gather"] += opnd.numel() * 2
+            if self.native:
+                mine = opnd.chunk(self.world, 0)[self.rank]
+                self._gather.append(dist.all_gather_into_tensor(opnd, mine, group=self.group, async_op=True))
+            else:
+                per = panel.size(0) // self.world
+                parts = [torch.empty_like(opnd[:per]) for _ in range(self.world)]
+                dist.all_gather(parts, opnd[self.rank * per:(self.rank + 1) * per].contiguous(), group=self.group)
+                for r, t in enumerate(parts):
+                    opnd[r * per:(r + 1) * per].copy_(t)
+        if self._rs:
+            self.master_stale = True
+            lay: Dict[str, List[Tuple[int, int]]] = {}
+            for key, panel, row0, _ in self._rs:
+                lay.setdefault(key, []).append((row0, row0 + panel.size(0)))
+            self._layout = lay
+        self._rs.clear()
+
+    def operand_gate(self) -> None:
+        """engine.operand_gate: the current stream waits for the operand all-gathers before the first GEMM reads them."""
+        for w in self._gather:
+            w.wait()
+        self._gather.clear()
+
+    def gather_rows(self, t: torch.Tensor, key: str) -> None:
+        """All-gathers (in place, blocking the stream) the rows of a [rows, cols] tensor laid out like parameter `key`:
+        every rank contributes the rows it owns."""
+        for lo, hi in self._panel_ranges(key):
+            blk = t[lo:hi]
+            if self.native:
+                dist.all_gather_into_tensor(blk, blk.chunk(self.world, 0)[self.rank], group=self.group)
+            else:
+                per = (hi - lo) // self.world
+                parts = [torch.empty_like(blk[:per]) for _ in range(self.world)]
+                dist.all_gather(parts, blk[self.rank * per:(self.rank + 1) * per].contiguous(), group=self.group)
+                for r, part in enumerate(parts):
+                    blk[r * per:(r + 1) * per].copy_(part)
+
+    def sync_master(self) -> None:
+        """Brings the fp32 master rows owned by other ranks up to date (checkpoint / state_dict time, or before the
+        operands are re-cast from the masters).  Collective: every rank must call it."""
+        if not self.master_stale or self.world == 1:
+            return
+        self.operand_gate()
+        for key in sorted(self.sharded):      # same order on every rank (set iteration order is per-process)
+            self.gather_rows(self.master[key].detach(), key)
+        self.master_stale = False
+
+    def _panel_ranges(self, key: str) -> List[Tuple[int, int]]:
+        """Panel layout of a sharded parameter as last exchanged (kept so that sync_master can run between steps)."""
+        return self._layout.get(key, [(0, self.master[key].size(0))])

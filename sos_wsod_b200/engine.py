@@ -25,7 +25,7 @@ from . import ops
 @dataclass
 class HeadConfig:
     num_classes: int = 20
-    refine_k: int = 3
+    refine_k: int = 4                 # WSL.REFINE_NUM of every code_release yaml (voc07_oicr_plus.yaml:56-58)
     pooled: int = 7
     spatial_scale: float = 1.0 / 8
     in_channels: int = 512
@@ -87,6 +87,7 @@ class HeadOperands:
         self.wh = torch.zeros((cfg.head_cols_padded, cfg.fc_dim), dtype=torch.bfloat16, device=dev)
         self.bh = torch.zeros((cfg.head_cols_padded,), dtype=torch.float32, device=dev)
         self._versions = None
+        self.pre_refresh = None     # callable run before a re-cast (a sharded optimizer brings the fp32 masters up to date)
         self.refresh()
 
     def head_slices(self) -> List[Tuple[str, str, int, int]]:
@@ -100,13 +101,38 @@ class HeadOperands:
         return out
 
     def _current_versions(self):
-        return tuple(t._version for t in self.master.values())
+        # (version counter, storage address): in-place updates bump the first, `param.data = ...` / module._apply
+        # (.float(), .to(), load with assign=True) change the second.  A write through `.data` IN PLACE changes neither:
+        # call invalidate() after one (EMA / LARS-style optimizers, manual weight surgery).
+        return tuple((t._version, t.data_ptr()) for t in self.master.values())
+
+    def invalidate(self) -> None:
+        """Forces the next refresh(force=False) to re-cast every operand."""
+        self._versions = None
+
+    def mark_fresh(self) -> None:
+        """Declares the operands up to date with the master parameters as they are now -- called by an optimizer that
+        wrote the bf16 copies itself in its update pass (solver.B200SGD)."""
+        self._versions = self._current_versions()
+
+    def sinks(self) -> Dict[int, Tuple[Optional[torch.Tensor], Optional[torch.Tensor]]]:
+        """id(master parameter) -> (bf16 operand view | None, fp32 copy view | None): where an optimizer that updates
+        the parameter in one pass has to put the refreshed GEMM operand (soswsod_sgd_multi's out_bf16 / out_f32)."""
+        m = self.master
+        out = {id(m["fc1_w"]): (self.w6, None), id(m["fc2_w"]): (self.w7, None),
+               id(m["fc1_b"]): (None, None), id(m["fc2_b"]): (None, None)}
+        for wk, bk, r0, n in self.head_slices():
+            out[id(m[wk])] = (self.wh[r0:r0 + n], None)
+            out[id(m[bk])] = (None, self.bh[r0:r0 + n])
+        return out
 
     def refresh(self, force: bool = True) -> None:
         """Re-casts the operands if any master parameter changed (optimizer step, checkpoint load)."""
         v = self._current_versions()
         if not force and v == self._versions:
             return
+        if self.pre_refresh is not None:
+            self.pre_refresh()
         m = self.master
         with torch.no_grad():
             ops.cast_f32_bf16(m["fc1_w"].detach(), out=self.w6)
@@ -153,7 +179,21 @@ class OICRPlusHeadEngine:
         self.deferred_scale_check = None
         self.last_output: Optional[TrainOutput] = None
         self.fc1_wgrad_panels = 4          # only with a grad_hook (data-parallel): see train_step
+        self.operand_gate = None           # callable: makes the current stream wait for in-flight operand updates
+        self.bias_on_side_stream = True    # bias-gradient column sums under the GEMMs (only without a grad_hook)
+        # engine-level training loops may let the step write the big weight gradients into the same buffers every
+        # step (the caller consumes them before the next step); never with autograd, which adopts the buffers as .grad
+        self.persistent_grads = False
+        self._grad_bufs: Dict[str, torch.Tensor] = {}
         self._side_stream = None
+
+    def _operands_ready(self):
+        """Called between the ROI pooling (which needs no weights) and the first GEMM: an operand all-gather of the
+        previous step's sharded update may still be in flight behind the pooling kernels (distributed.GradientExchange);
+        then re-cast whatever master parameter changed outside a fused optimizer step."""
+        if self.operand_gate is not None:
+            self.operand_gate()
+        self.op.refresh(force=False)
 
     def _side(self):
         if self._side_stream is None:
@@ -200,11 +240,12 @@ class OICRPlusHeadEngine:
         (get_image_level_gt, roi_heads.py:144-164); or, with `gt_count` / `gt_onehot` from ops.image_level_gt, the
         padded device list [C] whose live length stays on the device (no host synchronisation anywhere in the step).
         Gradients are those of loss_scale * sum(all loss keys).
-        grad_hook(name, [tensors]) is called as soon as the kernels producing a layer's parameter gradients are
-        queued -- the data-parallel caller starts that layer's NCCL all-reduce there, so it overlaps the remaining
-        backward kernels (the reference gets the same overlap from DDP buckets, tools/train_net_multi.py:75-78)."""
+        grad_hook(key, grad, row0) is called as soon as the kernel producing a parameter gradient is queued -- key is
+        "fc1_w" / "fc1_b" / "fc2_w" / "fc2_b" / "head_w" / "head_b" (the fused [cls | det | K x (cls_score, bbox_pred)]
+        block), `grad` the gradient or, for fc1_w, a panel of rows starting at row0.  The data-parallel caller
+        (distributed.GradientExchange) starts that tensor's collective there, so it overlaps the remaining backward
+        kernels (the reference gets the same overlap from DDP buckets, tools/train_net_multi.py:75-78)."""
         cfg, op = self.cfg, self.op
-        op.refresh(force=False)
         self.launches_last_step = 0
         C, K, V, R = cfg.num_classes, cfg.refine_k, vb.num_views, vb.R
         dev = vb.obj.device
@@ -219,6 +260,7 @@ class OICRPlusHeadEngine:
 
         # ---------------- forward ----------------
         X, argmaxes = self._pool(vb, keep_argmax=need_feat_grad)
+        self._operands_ready()
         H6, H7, L = self._trunk(X, True, dropout_seeds)
         ldp = cfg.head_cols_padded
         dL = torch.zeros((V * R, ldp), dtype=torch.float32, device=dev)
@@ -244,7 +286,16 @@ class OICRPlusHeadEngine:
         mscale = 1.0 / (1.0 - cfg.dropout_p) if cfg.dropout_p > 0 else 1.0
         # Bias gradients (column sums, HBM-bound, ~110 us per step) ride on a side stream under the tensor-bound GEMMs when
         # nobody needs them before the end of the step (no gradient hook); the main stream joins the side stream at the end.
-        side = self._side() if grad_hook is None else None
+        side = self._side() if (grad_hook is None and self.bias_on_side_stream) else None
+
+        def grad_buf(name, shape):
+            if not self.persistent_grads:
+                return None
+            t = self._grad_bufs.get(name)
+            if t is None or tuple(t.shape) != tuple(shape) or t.device != dev:
+                t = torch.empty(shape, dtype=torch.float32, device=dev)
+                self._grad_bufs[name] = t
+            return t
 
         def bias_grad(x):
             if side is None:
@@ -255,37 +306,42 @@ class OICRPlusHeadEngine:
                 side.wait_event(ev)
                 return ops.colsum(x)
 
-        dWh = ops.gemm_bf16(dLb, H7, a_mn=True, b_mn=True)                                          # [ldp, fc]
+        dWh = ops.gemm_bf16(dLb, H7, a_mn=True, b_mn=True, out=grad_buf("head_w", (ldp, cfg.fc_dim)))     # [ldp, fc]
         dbh_raw = bias_grad(dL)
         if grad_hook is not None:
             dbh = dbh_raw * col_scale
-            grad_hook("head", [dWh, dbh])
+            grad_hook("head_w", dWh, 0)
+            grad_hook("head_b", dbh, 0)
         dH7 = ops.gemm_bf16(dLb, op.wh, b_mn=True, out_dtype=torch.bfloat16, mask_src=H7, mask_scale=mscale)
-        dW7 = ops.gemm_bf16(dH7, H6, a_mn=True, b_mn=True)
+        dW7 = ops.gemm_bf16(dH7, H6, a_mn=True, b_mn=True, out=grad_buf("fc2_w", (cfg.fc_dim, cfg.fc_dim)))
         db7 = bias_grad(dH7)
         if grad_hook is not None:
-            grad_hook("fc2", [dW7, db7])
+            grad_hook("fc2_w", dW7, 0)
+            grad_hook("fc2_b", db7, 0)
         dH6 = ops.gemm_bf16(dH7, op.w7, b_mn=True, out_dtype=torch.bfloat16, mask_src=H6, mask_scale=mscale)
         panels = self.fc1_wgrad_panels if grad_hook is not None else 1
         if panels > 1 and cfg.fc_dim % (128 * panels) == 0:
-            # data-parallel: fc6's weight gradient (411 MB, 85 % of the all-reduce bytes) is produced in row panels and
-            # every panel's all-reduce starts as soon as its GEMM is queued, so the exchange overlaps the remaining
+            # data-parallel: fc6's weight gradient (411 MB, 85 % of the exchanged bytes) is produced in row panels and
+            # every panel's collective starts as soon as its GEMM is queued, so the exchange overlaps the remaining
             # panels, the fc6 dgrad and the ROI backward instead of starting only after the whole 1.2 ms GEMM.  A
             # panel = the same tiles the single launch would compute (bit-identical result).
-            dW6 = torch.empty((cfg.fc_dim, cfg.in_dim), dtype=torch.float32, device=dev)
+            dW6 = grad_buf("fc1_w", (cfg.fc_dim, cfg.in_dim))
+            if dW6 is None:
+                dW6 = torch.empty((cfg.fc_dim, cfg.in_dim), dtype=torch.float32, device=dev)
             rows = cfg.fc_dim // panels
             for pi in range(panels):
                 m0 = pi * rows
                 ops.gemm_bf16(dH6[:, m0:m0 + rows], X, a_mn=True, b_mn=True, out=dW6[m0:m0 + rows])
-                grad_hook("fc1", [dW6[m0:m0 + rows]])
+                grad_hook("fc1_w", dW6[m0:m0 + rows], m0)
             db6 = ops.colsum(dH6)
-            grad_hook("fc1", [db6])
+            grad_hook("fc1_b", db6, 0)
             self.launches_last_step += panels - 1
         else:
-            dW6 = ops.gemm_bf16(dH6, X, a_mn=True, b_mn=True)
+            dW6 = ops.gemm_bf16(dH6, X, a_mn=True, b_mn=True, out=grad_buf("fc1_w", (cfg.fc_dim, cfg.in_dim)))
             db6 = bias_grad(dH6)
             if grad_hook is not None:
-                grad_hook("fc1", [dW6, db6])
+                grad_hook("fc1_w", dW6, 0)
+                grad_hook("fc1_b", db6, 0)
         self.launches_last_step += 9
         grad_feats: List[torch.Tensor] = []
         if need_feat_grad:
@@ -316,10 +372,10 @@ class OICRPlusHeadEngine:
         """_forward_box_test for V views at once -> (probs [V,R,C+1], pred_boxes [V,R,4C]) in each view's own
         coordinates (predict_probs_K / predict_boxes_K, fast_rcnn_oicr.py:674-735)."""
         cfg, op = self.cfg, self.op
-        op.refresh(force=False)
         self.launches_last_step = 0
         C, K, V, R = cfg.num_classes, cfg.refine_k, vb.num_views, vb.R
         X, _ = self._pool(vb, keep_argmax=False)
+        self._operands_ready()
         _, _, L = self._trunk(X, False, (0, 0))
         boxes = vb.view_boxes().reshape(V * R, 4)
         probs, pred_boxes = ops.predict(L, cfg.col_ref0, cfg.ref_stride, boxes, C, K, cfg.bbox_reg_weights)

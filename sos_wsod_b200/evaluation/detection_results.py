@@ -69,6 +69,21 @@ class PascalVOCDetectionWriter:
                 ymin += 1
                 self._predictions[cls].append(f"{image_id} {score:.3f} {xmin:.1f} {ymin:.1f} {xmax:.1f} {ymax:.1f}")
 
+    def process_arrays(self, image_ids: Sequence[int], boxes: np.ndarray, scores: np.ndarray, classes: np.ndarray,
+                       counts: np.ndarray) -> None:
+        """`process` for a block of images whose detections were brought to the host in ONE copy: boxes float32
+        [n, topk, 4], scores float32 [n, topk], classes int [n, topk], counts int [n] (soswsod_detect's fixed-size
+        outputs).  Same float32 `+1` and the same string formatting as `process`."""
+        boxes = np.asarray(boxes, dtype=np.float32)
+        for i, image_id in enumerate(image_ids):
+            n = int(counts[i])
+            sc = [float(x) for x in scores[i, :n]]
+            for box, score, cls in zip(boxes[i, :n], sc, classes[i, :n].tolist()):
+                xmin, ymin, xmax, ymax = box
+                xmin += 1
+                ymin += 1
+                self._predictions[cls].append(f"{image_id} {score:.3f} {xmin:.1f} {ymin:.1f} {xmax:.1f} {ymax:.1f}")
+
     def rows(self, all_predictions: Optional[List[dict]] = None) -> List[dict]:
         merged: Dict[int, List[str]] = {}
         for p in (all_predictions if all_predictions is not None else [self._predictions]):

@@ -39,16 +39,19 @@ class _FusedHeadStep(Function):
     stored gradients to autograd in backward.  Inputs: feats..., then the parameters in HeadOperands.master order."""
 
     @staticmethod
-    def forward(ctx, engine, vb, gt_int, seeds, n_feats, *tensors):
+    def forward(ctx, engine, vb, gt_int, seeds, n_feats, loss_scale, *tensors):
         feats = tensors[:n_feats]
         need_fg = any(f.requires_grad for f in feats)
         gt_count = gt_onehot = None
         if isinstance(gt_int, tuple):      # (padded list, count, one-hot) kept on the device
             gt_int, gt_count, gt_onehot = gt_int
         out = engine.train_step(ViewBatch([f.detach() for f in feats], vb.rois, vb.obj, vb.R), gt_int, seeds,
-                                need_feat_grad=need_fg, grad_hook=engine.grad_hook, gt_count=gt_count, gt_onehot=gt_onehot)
+                                need_feat_grad=need_fg, loss_scale=loss_scale, grad_hook=engine.grad_hook,
+                                gt_count=gt_count, gt_onehot=gt_onehot)
         ctx.engine_out = out
+        ctx.exchange = getattr(engine, "exchange", None)
         ctx.deferred = engine.deferred_scale_check
+        ctx.loss_scale = float(loss_scale)
         ctx.n_feats = n_feats
         ctx.keys = list(engine.op.master.keys())
         ctx.loss_keys = list(out.losses.keys())
@@ -59,20 +62,29 @@ class _FusedHeadStep(Function):
     @once_differentiable
     def backward(ctx, *gouts):
         out = ctx.engine_out
+        if out is None:
+            raise RuntimeError("OICRPlusHeads: backward ran twice through one fused head step (retain_graph=True / a second "
+                               ".backward()); the step hands its gradient buffers to autograd once -- run forward again")
+        if ctx.exchange is not None:
+            # the gradient collectives started from the engine's hook run on NCCL's stream: order this stream behind
+            # them BEFORE autograd touches the buffers (AccumulateGrad adopts them, or clones them when it cannot)
+            ctx.exchange.wait_gradients()
         gs = torch.stack([x.reshape(()) for x in gouts])
+        pre = ctx.loss_scale        # the gradients were produced for pre * sum(losses) (heads.expected_loss_scale)
         if ctx.deferred is not None:
-            # upstream gradients are checked to be all 1 (the reference trainer's `sum(loss_dict.values()).backward()`,
-            # tools/train_net_multi.py:139) WITHOUT stalling the host: the values go to pinned memory behind an event
-            # and OICRPlusHeads.check_deferred() / the next forward raises if they were anything else
-            ctx.deferred.push(gs)
-            g = [1.0] * len(gouts)
+            # upstream gradients are checked to equal the expected scale (1 for the reference trainer's
+            # `sum(loss_dict.values()).backward()`, tools/train_net_multi.py:139) WITHOUT stalling the host: the values
+            # go to pinned memory behind an event and OICRPlusHeads.check_deferred() / the next forward raises if they
+            # were anything else
+            ctx.deferred.push(gs, pre)
+            s = 1.0
         else:
             g = gs.tolist()     # one tiny D2H read (host waits for the step)
-        if any(abs(v - g[0]) > 1e-12 * max(1.0, abs(g[0])) for v in g):
-            raise NotImplementedError(
-                "the fused OICR+ head step produces the gradient of s * sum(loss_dict.values()) -- the reference "
-                "trainer's objective (tools/train_net_multi.py:139); per-key loss weights are not supported")
-        s = g[0]
+            if any(abs(v - g[0]) > 1e-12 * max(1.0, abs(g[0])) for v in g):
+                raise NotImplementedError(
+                    "the fused OICR+ head step produces the gradient of s * sum(loss_dict.values()) -- the reference "
+                    "trainer's objective (tools/train_net_multi.py:139); per-key loss weights are not supported")
+            s = g[0] / pre if pre != 0.0 else 0.0
         def sc(t):
             return t if s == 1.0 else t * s
         gf = [sc(t) for t in out.grad_feats] if out.grad_feats else [None] * ctx.n_feats
@@ -82,7 +94,7 @@ class _FusedHeadStep(Function):
         ctx.engine_out = None
         out.grads = {}
         out.grad_feats = []
-        return (None, None, None, None, None, *gf, *gp)
+        return (None, None, None, None, None, None, *gf, *gp)
 
 
 class _DeferredScaleCheck:
@@ -91,25 +103,27 @@ class _DeferredScaleCheck:
     def __init__(self):
         self.pending = []
 
-    def push(self, gs: torch.Tensor) -> None:
+    def push(self, gs: torch.Tensor, expected: float) -> None:
         host = torch.empty(gs.shape, dtype=gs.dtype, pin_memory=True)
         host.copy_(gs, non_blocking=True)
         ev = torch.cuda.Event()
         ev.record()
-        self.pending.append((host, ev))
+        self.pending.append((host, ev, float(expected)))
 
     def check(self, wait: bool) -> None:
         keep = []
-        for host, ev in self.pending:
+        for host, ev, expected in self.pending:
             if not wait and not ev.query():
-                keep.append((host, ev))
+                keep.append((host, ev, expected))
                 continue
             ev.synchronize()
-            if not bool(torch.all(host == 1.0)):
+            if not bool(torch.all((host - expected).abs() <= 1e-6 * max(1.0, abs(expected)))):
                 self.pending = []
                 raise NotImplementedError(
-                    "loss_scale_check='deferred' requires the reference trainer's objective, sum(loss_dict.values())"
-                    f".backward() with unit upstream gradient; a previous backward received {host.tolist()}")
+                    "loss_scale_check='deferred': a previous backward received the upstream gradients "
+                    f"{host.tolist()} but the step was run for {expected} * sum(loss_dict.values()).  Set "
+                    "heads.expected_loss_scale to the factor applied to the summed loss (AMP GradScaler scale, "
+                    "1 / ITER_SIZE), or use loss_scale_check='sync'.  The gradients of that step were WRONGLY scaled.")
         self.pending = keep
 
 
@@ -148,12 +162,18 @@ class OICRPlusHeads(nn.Module):
         self.cls_agnostic_bbox_reg = cls_agnostic_bbox_reg
         self.reproduce_flip_quirk = True     # roi_heads_oicrplus.py:381; set False to use the flipped logits
         self._engine: Optional[OICRPlusHeadEngine] = None
-        # data-parallel callers set this to start a layer's gradient all-reduce as soon as it is produced
+        # data-parallel: grad_hook(key, grad, row0) starts a gradient's collective as soon as it is produced; normally
+        # installed by set_gradient_exchange()
         self.grad_hook = None
+        self.exchange = None
         self.last_metrics: Dict[str, torch.Tensor] = {}
         # "sync": backward reads the upstream gradients on the host (exact, stalls the host once per step);
         # "deferred": assumes sum(loss_dict.values()).backward() and verifies it one step late, without a stall
         self.loss_scale_check = "sync"
+        # the factor the caller applies to sum(loss_dict.values()) before .backward() (AMP GradScaler scale, 1 / ITER_SIZE
+        # gradient accumulation): the fused step produces its gradients already multiplied by it (free: folded into the
+        # logit-gradient cast); "sync" corrects any other value exactly, "deferred" verifies it one step late
+        self.expected_loss_scale = 1.0
         self._deferred = _DeferredScaleCheck()
         # image-level labels of CUDA targets are derived on the device (soswsod_image_level_gt); False restores the
         # reference's torch.unique call (identical values, one host synchronisation per step)
@@ -161,8 +181,37 @@ class OICRPlusHeads(nn.Module):
         self._gt_dev = None
 
     # ---- construction from config (roi_heads_oicrplus.py:88-147) ----
+    @staticmethod
+    def check_config(cfg) -> None:
+        """Every flag that changes the reference's arithmetic is either honoured or refused here, at construction:
+        the fused kernels implement the released OICR+ configuration and nothing may silently fall back to it."""
+        W, H, B = cfg.WSL, cfg.MODEL.ROI_HEADS, cfg.MODEL.ROI_BOX_HEAD
+
+        def refuse(cond, what):
+            if cond:
+                raise NotImplementedError(f"OICRPlusHeads (sm_100a fused path): {what}")
+
+        refuse(cfg.get("OICRPLUS", {}).get("BBOX_UPDATE", False),
+               "OICRPLUS.BBOX_UPDATE: True (delta-averaged pseudo-box update, roi_heads_oicrplus.py:397-425) is not "
+               "built; it is False in every released config")
+        refuse(B.get("BBOX_REG_LOSS_TYPE", "smooth_l1") != "smooth_l1" or float(B.get("SMOOTH_L1_BETA", 0.0)) != 0.0,
+               "the box-regression loss is the released smooth_l1 with SMOOTH_L1_BETA 0.0 (= L1, fast_rcnn_oicr.py:309-318); "
+               f"got {B.get('BBOX_REG_LOSS_TYPE')} / beta {B.get('SMOOTH_L1_BETA')}")
+        refuse(float(B.get("BBOX_REG_LOSS_WEIGHT", 1.0)) != 1.0, "BBOX_REG_LOSS_WEIGHT must be 1.0 (per-key loss weights are "
+               "not supported by the fused backward)")
+        refuse(not W.get("MEAN_LOSS", True), "WSL.MEAN_LOSS: False (sum-reduced BCE, fast_rcnn_wsddn.py:340-358) is not built")
+        refuse(list(H.get("IOU_LABELS", [0, -1, 1])) != [0, -1, 1] or len(H.IOU_THRESHOLDS) != 2,
+               "MODEL.ROI_HEADS.IOU_LABELS must be [0, -1, 1] with two IOU_THRESHOLDS (matcher.py:63-111)")
+        refuse(H.get("PROPOSAL_APPEND_GT", False), "PROPOSAL_APPEND_GT: True is not built (False in Base-RCNN-DilatedC5.yaml:15)")
+        refuse(B.get("CLS_AGNOSTIC_BBOX_REG", False), "class-agnostic box regression is not built")
+        refuse(not W.REFINE_MIST or W.MIST_TYPE != "nms", "only REFINE_MIST: True with MIST_TYPE: nms is built")
+        refuse(not all(bool(x) for x in list(W.REFINE_REG)[:W.REFINE_NUM]) or len(W.REFINE_REG) < W.REFINE_NUM,
+               "WSL.REFINE_REG must be True for every refinement branch")
+        refuse(B.POOLER_TYPE != "ROIPool", f"POOLER_TYPE {B.POOLER_TYPE} (only ROIPool is on the OICR+ path)")
+
     @classmethod
     def from_config(cls, cfg, input_shape: Dict[str, ShapeSpec]):
+        cls.check_config(cfg)
         in_features = cfg.MODEL.ROI_HEADS.IN_FEATURES
         res = cfg.MODEL.ROI_BOX_HEAD.POOLER_RESOLUTION
         scale = 1.0 / input_shape[in_features[-1]].stride
@@ -209,9 +258,30 @@ class OICRPlusHeads(nn.Module):
             self._engine = OICRPlusHeadEngine(hc, op)
         self._engine.cfg.reproduce_flip_quirk = self.reproduce_flip_quirk
         self._engine.grad_hook = self.grad_hook
+        self._engine.exchange = self.exchange
+        self._engine.operand_gate = self.exchange.operand_gate if self.exchange is not None else None
+        self._engine.op.pre_refresh = self.exchange.sync_master if self.exchange is not None else None
         assert self.loss_scale_check in ("sync", "deferred")
         self._engine.deferred_scale_check = self._deferred if self.loss_scale_check == "deferred" else None
         return self._engine
+
+    def set_gradient_exchange(self, mode: str = "sharded", group=None):
+        """Data-parallel training (one image per GPU, tools/train_net_multi.py:75-78 wraps the model in DDP): installs a
+        distributed.GradientExchange on this head -- its hook starts every gradient's collective from inside the
+        backward, `backward()` returns only after ordering the stream behind them, and an attached solver.B200SGD
+        finishes the exchange (sharded update + operand all-gather).  Returns the exchange."""
+        from ..distributed import GradientExchange
+
+        eng = self.engine()
+        self.exchange = GradientExchange(eng.op.master, group=group, mode=mode)
+        self.grad_hook = self.exchange.hook if self.exchange.world > 1 else None
+        self.engine()
+        return self.exchange
+
+    def state_dict(self, *args, **kwargs):
+        if self.exchange is not None:
+            self.exchange.sync_master()      # rows updated by other ranks (sharded optimizer) -> current fp32 values
+        return super().state_dict(*args, **kwargs)
 
     def image_level_gt_lists(self):
         """(gt_classes_img, gt_classes_img_int, gt_classes_img_oh) exactly as get_image_level_gt returns them, for the
@@ -221,6 +291,35 @@ class OICRPlusHeads(nn.Module):
             g = lst[:int(cnt.item())].to(torch.int64)
             return [g], [g], oh[None]
         return self.gt_classes_img, self.gt_classes_img_int, self.gt_classes_img_oh
+
+    def metric_scalars(self) -> Dict[str, float]:
+        """The scalars the reference's step leaves in its EventStorage, under the reference's names, from the counters
+        of the last training forward (one small device->host read; call it at the logging period):
+          roi_head/num_{fg,bg,ig}_samples_r{k}            wsl/modeling/roi_heads/roi_heads.py:364-373
+          fast_rcnn/{cls_accuracy,fg_cls_accuracy,false_negative}_r{k}   fast_rcnn_oicr.py:228-256
+        `_log_accuracy` runs once per view and a storage keeps the LAST value written, i.e. the one of view "2_flip"
+        (which, :381, is evaluated on view 2's logits) -- reproduced here."""
+        if not self.last_metrics:
+            return {}
+        acc = self.last_metrics["acc_counts"].cpu()       # [K, V, 5]: rows, fg, accurate, fg accurate, false negatives
+        lab = self.last_metrics["label_counts"].cpu()     # [K, 3]: fg, bg, ignored
+        out: Dict[str, float] = {}
+        for k in range(acc.size(0)):
+            out[f"roi_head/num_fg_samples_r{k}"] = float(lab[k, 0])
+            out[f"roi_head/num_bg_samples_r{k}"] = float(lab[k, 1])
+            out[f"roi_head/num_ig_samples_r{k}"] = float(lab[k, 2])
+            n, n_fg, n_acc, n_fgacc, n_fn = (int(x) for x in acc[k, -1])
+            if n > 0:
+                out[f"fast_rcnn/cls_accuracy_r{k}"] = n_acc / n
+                if n_fg > 0:
+                    out[f"fast_rcnn/fg_cls_accuracy_r{k}"] = n_fgacc / n_fg
+                    out[f"fast_rcnn/false_negative_r{k}"] = n_fn / n_fg
+        return out
+
+    def log_metrics(self, storage) -> None:
+        """storage: anything with put_scalar(name, value) -- detectron2's EventStorage."""
+        for k, v in self.metric_scalars().items():
+            storage.put_scalar(k, v)
 
     def check_deferred(self, wait: bool = True) -> None:
         """Raises if a backward run under loss_scale_check='deferred' saw a non-unit upstream gradient."""
@@ -273,12 +372,15 @@ class OICRPlusHeads(nn.Module):
         assert len(proposals1) == 1, "the reference trains with one image per GPU (rcnn_multi.py:148)"
         eng = self.engine()
         self._deferred.check(wait=False)
+        if self.exchange is not None:
+            self.exchange.begin_step()
         rois, obj = self._view_rois([[proposals1[0], proposals1_flip[0]], [proposals2[0], proposals2_flip[0]]])
         R = len(proposals1[0])
         vb = ViewBatch([features1, features2], rois, obj, R)
         seeds = (torch.initial_seed() * 7919 + 2 * self.iter + 1, torch.initial_seed() * 7919 + 2 * self.iter + 2)
         gt_arg = self._gt_dev if self._gt_dev is not None else self.gt_classes_img_int[0]
-        outs = _FusedHeadStep.apply(eng, vb, gt_arg, seeds, 2, features1, features2, *self._param_list())
+        outs = _FusedHeadStep.apply(eng, vb, gt_arg, seeds, 2, float(self.expected_loss_scale), features1, features2,
+                                    *self._param_list())
         out = eng.last_output
         self.last_metrics = {"acc_counts": out.aux["acc_counts"], "label_counts": out.aux["counts"]}
         return dict(zip(out.losses.keys(), outs))

@@ -121,7 +121,13 @@ class DatasetMapperTTAAVG:
 
     def transform_proposals(self, proposals: Instances, specs: Sequence[ViewSpec], min_box_size: float = 0.0):
         """transform_proposals (:29-71) for every view at once.  Returns (list of per-view Instances on the device,
-        dropped int32 [V] on the device).  A view's Instances keeps ALL rows (see ops.tta_views)."""
+        dropped int32 [V] on the device).
+
+        The reference filters the empty boxes of a view FIRST and then keeps `boxes[keep][:topk]` (:62-71).  When no
+        row among the first `topk` becomes empty in any view -- the normal case: integer proposals scaled up stay
+        non-empty -- that is exactly the first `topk` rows, which is what this fast path returns without a host
+        synchronisation; `dropped[v]` counts the empty rows among them, and a non-zero count sends the caller to
+        `transform_proposals_exact` (the reference's back-filled selection)."""
         boxes = proposals.proposal_boxes.tensor
         logits = proposals.objectness_logits
         if self.proposal_topk is not None:
@@ -138,6 +144,27 @@ class DatasetMapperTTAAVG:
             inst.objectness_logits = logits
             out.append(inst)
         return out, dropped
+
+    def transform_proposals_exact(self, proposals: Instances, specs: Sequence[ViewSpec], min_box_size: float = 0.0):
+        """The reference's order of operations (:57-71) when some row does become empty: per view, transform + clip ALL
+        rows, drop the empty ones, THEN take the first `topk` survivors -- so a view back-fills from the rows behind
+        `topk` and the views may hold different proposals at the same row index (the reference averages them row by row
+        all the same, :367-372).  One host synchronisation (the selections have data-dependent sizes)."""
+        boxes = proposals.proposal_boxes.tensor.to(self.device)
+        logits = proposals.objectness_logits.to(self.device)
+        rois, keep, _ = ops.tta_views(boxes, [s.params(0.0) for s in specs], min_box_size)
+        R = boxes.size(0)
+        rois = rois.view(len(specs), R, 5)
+        out = []
+        for v, s in enumerate(specs):
+            sel = keep[v].nonzero().flatten()
+            if self.proposal_topk is not None:
+                sel = sel[: self.proposal_topk]
+            inst = Instances(s.image_size)
+            inst.proposal_boxes = Boxes(rois[v, sel, 1:5].contiguous())
+            inst.objectness_logits = logits[sel]
+            out.append(inst)
+        return out
 
     def __call__(self, dataset_dict):
         numpy_image = dataset_dict["image"].permute(1, 2, 0).numpy()
@@ -280,20 +307,18 @@ class GeneralizedRCNNWithTTAAVG(nn.Module):
         return {"instances": merged_instances}
 
     def _inference_with_dropped_proposals(self, input, tfms):
-        """Some proposal became empty in some view.  The reference drops it from THAT view only (:62-64) and then
-        fails in torch.cat / mean unless every view dropped the same rows; reproduce both outcomes."""
+        """Some proposal among the rows in use became empty in some view: redo the image with the reference's exact
+        selection (filter per view, then top-k, :57-71).  Views that end up with different row counts cannot be
+        averaged by the reference either (torch.cat / mean of unequal shapes, :367)."""
         mapper = self.tta_mapper
-        p = input["proposals"]
-        boxes = p.proposal_boxes.tensor[: mapper.proposal_topk].to(mapper.device)
-        _, keep, _ = ops.tta_views(boxes, [t.params() for t in tfms])
-        common = keep.all(dim=0)
-        if not bool((keep == common[None]).all()):
-            raise RuntimeError("TTA views keep different proposal rows after clip/nonempty: the reference cannot average "
-                               "them either (test_time_augmentation_avg.py:367: torch.cat of unequal shapes)")
-        kept = common.nonzero().flatten().cpu()
-        filtered = Instances(p.image_size)
-        filtered.proposal_boxes = Boxes(p.proposal_boxes.tensor[: mapper.proposal_topk][kept])
-        filtered.objectness_logits = p.objectness_logits[: mapper.proposal_topk][kept]
-        inp = dict(input)
-        inp["proposals"] = filtered
-        return self._inference_one_image(inp)
+        props = mapper.transform_proposals_exact(input["proposals"], tfms)
+        counts = {len(p) for p in props}
+        if len(counts) != 1:
+            raise RuntimeError("TTA views keep different numbers of proposals after clip/nonempty: the reference cannot "
+                               f"average them either (test_time_augmentation_avg.py:367); rows per view = {sorted(counts)}")
+        augmented_inputs, tfms2 = self._get_augmented_inputs(input)
+        for x, p in zip(augmented_inputs, props):
+            x["proposals"] = p
+            x.pop("proposals_dropped", None)
+        all_boxes, all_scores, _ = self._get_augmented_boxes(augmented_inputs, tfms2)
+        return {"instances": self._merge_detections(all_boxes, all_scores, None, (input["height"], input["width"]))}

@@ -138,6 +138,7 @@ def roi_pool_backward(grad_out: torch.Tensor, argmax: torch.Tensor, rois: torch.
 # (2) GEMM + helpers
 # ------------------------------------------------------------------------------------------------
 _GEMM_SCHED = {}
+GEMM_SCHED_SLOTS = 1     # > 1: launches on a stream rotate through that many scheduler workspaces (diagnosis only)
 
 
 def _gemm_sched(device) -> torch.Tensor:
@@ -145,10 +146,11 @@ def _gemm_sched(device) -> torch.Tensor:
     stream: launches on one stream are ordered and share it, other streams get their own."""
     key = (device.index, torch.cuda.current_stream(device).cuda_stream)
     t = _GEMM_SCHED.get(key)
-    if t is None:
-        t = torch.zeros(2, dtype=torch.int32, device=device)
+    if t is None or t[0].size(0) != GEMM_SCHED_SLOTS:
+        t = [torch.zeros((GEMM_SCHED_SLOTS, 4), dtype=torch.int32, device=device), 0]
         _GEMM_SCHED[key] = t
-    return t
+    t[1] = (t[1] + 1) % GEMM_SCHED_SLOTS
+    return t[0][t[1]]
 
 
 def gemm_bf16(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool = False,
@@ -253,6 +255,38 @@ def sgd_step(param: torch.Tensor, grad: torch.Tensor, buf: torch.Tensor, lr: flo
     check(_lib.load().soswsod_sgd_step(_ptr(param), _ptr(grad), _ptr(buf), param.numel(), float(lr), float(momentum),
                                        float(weight_decay), float(grad_scale), _ptr(param_bf16), _stream()), "sgd_step")
     _count(1)
+
+
+def sgd_multi(items, momentum: float, grad_scale: float = 1.0) -> int:
+    """One fused SGD(+momentum, weight decay) launch per 32 tensors.  items: iterable of
+    (param, grad, momentum_buf, lr, weight_decay, out_bf16 | None, out_f32 | None); every tensor contiguous, fp32
+    (out_bf16 bf16), same numel.  Shards are passed as views.  Returns the number of launches."""
+    import ctypes
+
+    items = list(items)
+    lib = _lib.load()
+    n_launch = 0
+    for i0 in range(0, len(items), _lib.SGD_MAX_TENSORS):
+        chunk = items[i0:i0 + _lib.SGD_MAX_TENSORS]
+        arr = (_lib.SgdTensor * len(chunk))()
+        for d, (p, g, buf, lr, wd, ob, of) in zip(arr, chunk):
+            _need_cuda(p, g, buf, ob, of)
+            n = p.numel()
+            if not (p.is_contiguous() and g.is_contiguous() and buf.is_contiguous() and g.numel() == n and buf.numel() == n
+                    and p.dtype == g.dtype == buf.dtype == torch.float32):
+                raise RuntimeError("sgd_multi: param / grad / momentum_buf must be contiguous fp32 tensors of one size")
+            if ob is not None and not (ob.is_contiguous() and ob.dtype == torch.bfloat16 and ob.numel() == n):
+                raise RuntimeError("sgd_multi: out_bf16 must be a contiguous bf16 tensor of the parameter's size")
+            if of is not None and not (of.is_contiguous() and of.dtype == torch.float32 and of.numel() == n):
+                raise RuntimeError("sgd_multi: out_f32 must be a contiguous fp32 tensor of the parameter's size")
+            d.param, d.grad, d.momentum_buf = p.data_ptr(), g.data_ptr(), buf.data_ptr()
+            d.out_bf16, d.out_f32 = _ptr(ob), _ptr(of)
+            d.n, d.lr, d.weight_decay = n, float(lr), float(wd)
+        check(lib.soswsod_sgd_multi(ctypes.cast(arr, ctypes.c_void_p), len(chunk), float(momentum), float(grad_scale),
+                                    _stream()), "sgd_multi")
+        n_launch += 1
+    _count(n_launch)
+    return n_launch
 
 
 # ------------------------------------------------------------------------------------------------

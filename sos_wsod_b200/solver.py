@@ -3,9 +3,9 @@ over the fused SGD kernel: per parameter lr / weight dec
 WEIGHT_DECAY_BIAS, norm layers WEIGHT_DECAY_NORM, optional higher lr on the refinement branches), SGD with momentum
 exactly as torch.optim.SGD(momentum=m, dampening=0, nesterov=False) computes it:
     buf = m * buf + (grad + wd * p);  p -= lr * buf
-`B200SGD.step()` makes ONE pass over each parameter (soswsod_sgd_step reads p, grad, buf and writes p, buf) instead of
-torch's 3-4 elementwise passes; the head's bf16 GEMM operands refresh themselves on the next forward (parameter
-version counters).  Gradient clipping (SOLVER.CLIP_GRADIENTS) is off in every released OICR+ config and not built."""
+`B200SGD.step()` makes ONE pass over the parameters in ONE launch per 32 tensors (soswsod_sgd_multi reads p, grad, buf
+and writes p, buf) instead of torch's 3-4 elementwise passes per tensor, and -- attached to an OICRPlusHeads -- writes
+the head's bf16 GEMM operands in the same pass.  Gradient clipping (SOLVER.CLIP_GRADIENTS) is off in every released OICR+ config and not built."""
 from __future__ import annotations
 
 from typing import Any, Dict, List, Set
@@ -58,10 +58,39 @@ def get_optimizer_param_groups(cfg, model: torch.nn.Module) -> List[Dict[str, An
 
 
 class B200SGD(torch.optim.Optimizer):
-    """torch.optim.SGD(momentum, dampening=0, nesterov=False) semantics; state key `momentum_buffer` like torch's."""
+    """torch.optim.SGD(momentum, dampening=0, nesterov=False) semantics; state key `momentum_buffer` like torch's.
+    The whole step is ONE launch per 32 parameters (soswsod_sgd_multi).  With `attach_head(heads)` the same pass also
+    writes the head's bf16 GEMM operands (and the fused head-bias vector), so the next forward does not re-cast 121 M
+    weights (3 cast launches over 726 MB, engine.HeadOperands.refresh)."""
 
     def __init__(self, params, lr: float, momentum: float = 0.0, weight_decay: float = 0.0):
         super().__init__(params, dict(lr=lr, momentum=momentum, weight_decay=weight_decay))
+        self._heads = []
+        self.launches_last_step = 0
+
+    def attach_head(self, heads) -> "B200SGD":
+        """heads: an OICRPlusHeads whose parameters this optimizer updates."""
+        self._heads.append(heads)
+        return self
+
+    def sync_state(self) -> None:
+        """Sharded data-parallel update: a rank's momentum buffers are current only on the rows it owns; this gathers
+        the other rows (collective -- every rank calls it), e.g. before `state_dict()` for a checkpoint."""
+        for h in self._heads:
+            ex = getattr(h, "exchange", None)
+            if ex is None or ex.world == 1:
+                continue
+            ex.sync_master()
+            for key in sorted(ex.sharded):
+                st = self.state.get(ex.master[key], {})
+                if "momentum_buffer" in st:
+                    ex.gather_rows(st["momentum_buffer"], key)
+
+    def _sinks(self):
+        out = {}
+        for h in self._heads:
+            out.update(h.engine().op.sinks())
+        return out
 
     @torch.no_grad()
     def step(self, closure=None):
@@ -69,6 +98,18 @@ class B200SGD(torch.optim.Optimizer):
         if closure is not None:
             with torch.enable_grad():
                 loss = closure()
+        sinks = self._sinks()
+        self.launches_last_step = 0
+        # data-parallel heads: finish the gradient exchange; a sharded parameter is updated only on the rows this rank
+        # owns (their averaged gradient arrived by reduce-scatter), its bf16 operand rows are all-gathered afterwards
+        shard_rows = {}
+        for h in self._heads:
+            ex = getattr(h, "exchange", None)
+            if ex is not None and ex.world > 1:
+                ex.wait_gradients()
+                for key in sorted(ex.sharded):
+                    shard_rows[id(ex.master[key])] = ex.owned_rows(key)
+        by_momentum, touched = {}, []          # the reference makes one group per parameter: batch across groups
         for group in self.param_groups:
             for p in group["params"]:
                 if p.grad is None:
@@ -79,13 +120,30 @@ class B200SGD(torch.optim.Optimizer):
                 if "momentum_buffer" not in st:
                     st["momentum_buffer"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
                 grad = p.grad if p.grad.is_contiguous() else p.grad.contiguous()
-                w = p.detach()
-                if not w.is_contiguous():
+                if not p.is_contiguous():
                     raise RuntimeError("B200SGD needs contiguous parameters")
-                ops.sgd_step(w, grad, st["momentum_buffer"], group["lr"], group["momentum"], group["weight_decay"])
-                # the kernel wrote through the raw pointer: a one-element in-place no-op on a view bumps the shared
-                # version counter, which is what HeadOperands.refresh() watches to re-cast the bf16 GEMM operands
-                w.view(-1)[:1].add_(0.0)
+                ob, of = sinks.get(id(p), (None, None))
+                items = by_momentum.setdefault(float(group["momentum"]), [])
+                pd, buf = p.detach(), st["momentum_buffer"]
+                for lo, hi in shard_rows.get(id(p), [(0, p.size(0) if p.dim() else 1)]):
+                    whole = (lo == 0 and hi == (p.size(0) if p.dim() else 1))
+                    sl = (lambda t: t) if whole else (lambda t, lo=lo, hi=hi: None if t is None else t[lo:hi])
+                    items.append((sl(pd), sl(grad), sl(buf), group["lr"], group["weight_decay"], sl(ob), sl(of)))
+                touched.append(p)
+        for momentum, items in by_momentum.items():
+            self.launches_last_step += ops.sgd_multi(items, momentum)
+        for p in touched:
+            # the kernel wrote through raw pointers: bump the version counters like an in-place op would
+            torch.autograd.graph.increment_version(p)
+        for h in self._heads:
+            ex = getattr(h, "exchange", None)
+            if ex is not None and ex.world > 1:
+                op = h.engine().op
+                ex.gather_operands({"fc1_w": op.w6, "fc2_w": op.w7})
+        for h in self._heads:
+            op = h.engine().op
+            if all(p.grad is not None for p in op.master.values()):
+                op.mark_fresh()          # every operand was rewritten by this step
         return loss
 
 
@@ -96,4 +154,10 @@ def build_optimizer(cfg, model: torch.nn.Module) -> torch.optim.Optimizer:
     clip = S.get("CLIP_GRADIENTS", None)
     if clip is not None and clip.get("ENABLED", False):
         raise NotImplementedError("SOLVER.CLIP_GRADIENTS is not built (off in every released OICR+ config)")
-    return B200SGD(get_optimizer_param_groups(cfg, model), S.BASE_LR, momentum=S.MOMENTUM)
+    opt = B200SGD(get_optimizer_param_groups(cfg, model), S.BASE_LR, momentum=S.MOMENTUM)
+    from .modeling.roi_heads_oicrplus import OICRPlusHeads
+
+    for m in model.modules():
+        if isinstance(m, OICRPlusHeads) and next(m.parameters()).is_cuda:
+            opt.attach_head(m)
+    return opt

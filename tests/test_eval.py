@@ -84,6 +84,25 @@ def test_product_writers_are_byte_compatible(gold, tmp_path):
         coco.process([{"image_id": d["image_id"]}], [{"instances": _instances(d)}])
     assert open(voc.save()).read() == gold["voc_json"]
     assert open(coco.save()).read() == gold["coco_json"]
+    # the block path (one device->host copy for many images, fixed-size detect outputs) writes the same bytes
+    import numpy as np
+
+    per = list(_per_image(gold))
+    topk = max(len(d["scores"]) for d in per) + 3
+    boxes = np.zeros((len(per), topk, 4), np.float32)
+    scores = np.zeros((len(per), topk), np.float32)
+    classes = np.zeros((len(per), topk), np.int32)
+    counts = np.zeros((len(per),), np.int32)
+    for i, d in enumerate(per):
+        inst = _instances(d)
+        n = len(inst.scores)
+        counts[i] = n
+        boxes[i, :n] = inst.pred_boxes.tensor.numpy()
+        scores[i, :n] = inst.scores.numpy()
+        classes[i, :n] = inst.pred_classes.numpy()
+    voc2 = PascalVOCDetectionWriter("voc_2007_test", [f"c{k}" for k in range(gold["num_classes"])], str(tmp_path / "blk_{}.json"))
+    voc2.process_arrays([d["image_id"] for d in per], boxes, scores, classes, counts)
+    assert open(voc2.save()).read() == gold["voc_json"]
 
 
 _SHARD_SCRIPT = r'''

@@ -210,7 +210,7 @@ def test_plugin_surface_train_and_eval(cuda_lib):
     torch.manual_seed(0)
     cfg = get_cfg()
     cfg.MODEL.ROI_BOX_HEAD.DAN_DIM = [256, 256]
-    ch, R, C, K = 32, 200, 20, 3
+    ch, R, C, K = 32, 200, 20, cfg.WSL.REFINE_NUM
     heads = build_roi_heads(cfg, {"plain5": ShapeSpec(channels=ch, stride=8)}).cuda()
     for r in heads.box_refinery:
         r.cls_score.weight.data.mul_(20.0)
@@ -272,7 +272,27 @@ def test_plugin_surface_train_and_eval(cuda_lib):
     (2.0 * sum(l4.values())).backward()
     with pytest.raises(NotImplementedError):
         heads.check_deferred(wait=True)
+    # a declared loss scale (AMP GradScaler, 1 / ITER_SIZE): the deferred mode produces correctly scaled gradients
+    # and its late check passes; sync mode corrects an undeclared scale exactly
+    for prm in heads.parameters():
+        prm.grad = None
+    heads.iter -= 2
+    heads.expected_loss_scale = 0.25
+    _, l5 = heads(None, [{"plain5": f1}, {"plain5": f2}], [props(v) for v in views], [targets, None, None, None])
+    (0.25 * sum(l5.values())).backward()
+    heads.check_deferred(wait=True)
+    g_quarter = heads.box_head.fc2.weight.grad.clone()
+    heads.expected_loss_scale = 1.0
     heads.loss_scale_check = "sync"
+    for prm in heads.parameters():
+        prm.grad = None
+    heads.iter -= 1
+    _, l6 = heads(None, [{"plain5": f1}, {"plain5": f2}], [props(v) for v in views], [targets, None, None, None])
+    tot6 = 0.25 * sum(l6.values())
+    tot6.backward(retain_graph=True)
+    torch.testing.assert_close(heads.box_head.fc2.weight.grad, g_quarter, rtol=2e-2, atol=1e-6 * float(g_quarter.abs().max()) + 1e-9)
+    with pytest.raises(RuntimeError, match="backward ran twice"):
+        tot6.backward()
     # eval
     heads.eval()
     inst, empty, all_scores, all_boxes = heads(None, {"plain5": f1[:1].detach()}, props(views[0]), None)
@@ -358,19 +378,21 @@ def test_grad_hook_panels_are_bit_identical(cuda_lib):
     ref_out = eng.train_step(vb, gt_int)
     seen = []
 
-    def hook(name, tensors):
-        seen.append((name, [t.data_ptr() for t in tensors], sum(t.numel() for t in tensors)))
+    def hook(key, grad, row0):
+        seen.append((key, grad.data_ptr(), grad.numel(), row0))
 
     eng.fc1_wgrad_panels = 4
     out = eng.train_step(vb, gt_int, grad_hook=hook)
     for k in ref_out.grads:
         assert torch.equal(ref_out.grads[k], out.grads[k]), k
-    names = [n for n, _, _ in seen]
-    assert names == ["head", "fc2"] + ["fc1"] * 5
-    fc1_elems = sum(n for name, _, n in seen if name == "fc1")
-    assert fc1_elems == out.grads["fc1_w"].numel() + out.grads["fc1_b"].numel()
-    ptrs = [pp for name, ps, _ in seen if name == "fc1" for pp in ps]
-    assert len(set(ptrs)) == len(ptrs)
+    assert [s[0] for s in seen] == ["head_w", "head_b", "fc2_w", "fc2_b"] + ["fc1_w"] * 4 + ["fc1_b"]
+    rows = cfg.fc_dim // 4
+    assert [s[3] for s in seen if s[0] == "fc1_w"] == [0, rows, 2 * rows, 3 * rows]
+    assert sum(s[2] for s in seen if s[0] == "fc1_w") == out.grads["fc1_w"].numel()
+    base = out.grads["fc1_w"].data_ptr()
+    assert [s[1] for s in seen if s[0] == "fc1_w"] == [base + 4 * i * rows * cfg.in_dim for i in range(4)]
+    # the fused head block carries every output layer's gradient: one collective instead of 2 + 2K
+    assert [s[2] for s in seen if s[0] == "head_w"] == [cfg.head_cols_padded * cfg.fc_dim]
 
 
 class _TinyBackbone(torch.nn.Module):
@@ -487,3 +509,266 @@ def test_b200_sgd_matches_torch_sgd_and_refreshes_operands(cuda_lib):
     eng.train_step(vb, torch.unique(gt_classes).cuda())
     assert not torch.equal(eng.op.w7, w7_before)
     assert torch.equal(eng.op.w7, eng.op.master["fc2_w"].detach().to(torch.bfloat16))
+
+
+def test_b200_sgd_attached_writes_operands_in_the_update_pass(cuda_lib):
+    """Attached to the head, B200SGD.step() is one launch that also writes the bf16 GEMM operands and the fused
+    head-bias vector: bit-equal to re-casting the updated masters, and the next forward launches no cast kernel.
+    Operand staleness: `param.data = ...` is detected through the storage address, `invalidate()` covers
+    in-place `.data` writes."""
+    from sos_wsod_b200 import ops
+    from sos_wsod_b200.config import get_cfg
+    from sos_wsod_b200.modeling import build_roi_heads
+    from sos_wsod_b200.solver import build_optimizer
+    from sos_wsod_b200.structures import Boxes, Instances, ShapeSpec
+
+    torch.manual_seed(0)
+    cfg = get_cfg()
+    cfg.MODEL.ROI_BOX_HEAD.DAN_DIM = [256, 256]
+    ch, R = 32, 160
+    heads = build_roi_heads(cfg, {"plain5": ShapeSpec(channels=ch, stride=8)}).cuda().train()
+    opt = build_optimizer(cfg, heads)
+    assert opt._heads == [heads]
+    g = torch.Generator().manual_seed(3)
+    views = ref.synth_views(R, [(240, 320), (288, 384)], g, channels=ch)
+    f1 = torch.cat([views[0].feat, views[1].feat], 0).cuda()
+    f2 = torch.cat([views[2].feat, views[3].feat], 0).cuda()
+    props = [[Instances(v.image_size, proposal_boxes=Boxes(v.boxes.cuda()), objectness_logits=v.obj.cuda())] for v in views]
+    targets = [Instances(views[0].image_size, gt_classes=torch.tensor([2, 9]).cuda(), gt_boxes=Boxes(torch.zeros(2, 4).cuda()))]
+
+    def step():
+        opt.zero_grad()
+        _, losses = heads(None, [{"plain5": f1}, {"plain5": f2}], props, [targets, None, None, None])
+        sum(losses.values()).backward()
+        opt.step()
+
+    step()
+    assert opt.launches_last_step == 1
+    op = heads.engine().op
+    assert torch.equal(op.w6, heads.box_head.fc1.weight.detach().to(torch.bfloat16))
+    assert torch.equal(op.w7, heads.box_head.fc2.weight.detach().to(torch.bfloat16))
+    for wk, bk, r0, n in op.head_slices():
+        assert torch.equal(op.wh[r0:r0 + n], op.master[wk].detach().to(torch.bfloat16))
+        assert torch.equal(op.bh[r0:r0 + n], op.master[bk].detach())
+    # momentum buffers + second step equal torch.optim.SGD on a copy fed the same gradients
+    casts = {"n": 0}
+    orig = ops.cast_f32_bf16
+
+    def counting(*a, **k):
+        if k.get("out") is not None:
+            casts["n"] += 1
+        return orig(*a, **k)
+
+    ops.cast_f32_bf16 = counting
+    try:
+        step()
+        assert casts["n"] == 0, "operands written by the optimizer must not be re-cast by the next forward"
+        # storage replaced -> detected
+        with torch.no_grad():
+            heads.box_head.fc2.weight.data = heads.box_head.fc2.weight.data.clone() * 0.5
+        heads.engine().op.refresh(force=False)
+        assert casts["n"] > 0 and torch.equal(op.w7, heads.box_head.fc2.weight.detach().to(torch.bfloat16))
+        # in-place write through .data: invisible to the counters -> explicit invalidate()
+        n0 = casts["n"]
+        heads.box_head.fc2.weight.data.mul_(2.0)
+        op.refresh(force=False)
+        assert casts["n"] == n0
+        op.invalidate()
+        op.refresh(force=False)
+        assert casts["n"] > n0 and torch.equal(op.w7, heads.box_head.fc2.weight.detach().to(torch.bfloat16))
+    finally:
+        ops.cast_f32_bf16 = orig
+
+
+def test_sgd_multi_matches_torch_sgd(cuda_lib):
+    """soswsod_sgd_multi over ragged tensors (sizes not multiples of 4, unaligned views, shards) == torch.optim.SGD."""
+    from sos_wsod_b200 import ops
+
+    g = torch.Generator().manual_seed(1)
+    sizes = [1, 3, 4, 5, 4095, 4096, 4097, 10007, 3 * 4096 + 2]
+    ps = [torch.randn(n, generator=g).cuda() for n in sizes]
+    big = torch.randn(50001, generator=g).cuda()
+    ps.append(big[1:30000])          # misaligned view
+    ps.append(big[30000:50000])      # a shard of a larger tensor
+    ref_ps = [p.clone().requires_grad_(True) for p in ps]
+    lrs = [1e-3 * (1 + i % 3) for i in range(len(ps))]
+    wds = [0.0 if i % 2 else 5e-4 for i in range(len(ps))]
+    opt = torch.optim.SGD([{"params": [p], "lr": lr, "weight_decay": wd} for p, lr, wd in zip(ref_ps, lrs, wds)], 1e-3, momentum=0.9)
+    bufs = [torch.zeros_like(p).contiguous() for p in ps]
+    ps = [p.contiguous() if p.is_contiguous() else p for p in ps]
+    obs = [torch.empty(p.numel(), dtype=torch.bfloat16, device="cuda") if i % 2 == 0 else None for i, p in enumerate(ps)]
+    ofs = [torch.empty(p.numel(), dtype=torch.float32, device="cuda") if i % 3 == 0 else None for i, p in enumerate(ps)]
+    for it in range(3):
+        grads = [torch.randn(p.numel(), generator=g).cuda() for p in ps]
+        for rp, gr in zip(ref_ps, grads):
+            rp.grad = gr.clone()
+        opt.step()
+        n = ops.sgd_multi([(p, gr, b, lr, wd, ob, of) for p, gr, b, lr, wd, ob, of in zip(ps, grads, bufs, lrs, wds, obs, ofs)], 0.9)
+        assert n == 1
+    for p, rp, ob, of in zip(ps, ref_ps, obs, ofs):
+        torch.testing.assert_close(p, rp.detach(), rtol=1e-6, atol=1e-7)
+        if ob is not None:
+            assert torch.equal(ob, p.to(torch.bfloat16))
+        if of is not None:
+            assert torch.equal(of, p)
+    # 40 tensors -> two launches
+    many = [torch.zeros(7, device="cuda") for _ in range(40)]
+    assert ops.sgd_multi([(p, torch.ones_like(p), torch.zeros_like(p), 0.1, 0.0, None, None) for p in many], 0.0) == 2
+    assert all(torch.allclose(p, torch.full_like(p, -0.1)) for p in many)
+
+
+def test_step_matches_the_reference_forward_box_golden(cuda_lib):
+    """The engine against tests/golden/step_golden.pt = losses and gradients of the REFERENCE'S OWN
+    OICRPlusHeads.forward + backward (tests/golden/make_golden_step.py; dropout off).  The oracle, run on the same
+    inputs, reproduces that fixture to 1e-6 (tests/test_oracle.py); here the device must mine the same pseudo labels
+    and land within the bf16 tolerances of north_star on losses and gradients."""
+    import step_golden_util as sg
+    from sos_wsod_b200.engine import HeadConfig, HeadOperands, OICRPlusHeadEngine, ViewBatch
+    from sos_wsod_b200.synthetic import pack_views
+
+    for name in ("voc_k3", "coco_k4"):
+        case = sg.load()[name]
+        exp = case["eval_dropout"]
+        C, K, R = case["C"], case["K"], case["R"]
+        p = sg.head_params(case)
+        views = sg.views(case)
+        cfg = HeadConfig(num_classes=C, refine_k=K, in_channels=case["ch"], fc_dim=case["fc"], dropout_p=0.0)
+        op = HeadOperands(cfg, *[t.cuda() for t in (p.fc1_w, p.fc1_b, p.fc2_w, p.fc2_b, p.cls_w, p.cls_b, p.det_w, p.det_b)],
+                          [tuple(t.cuda() for t in r) for r in p.refine])
+        eng = OICRPlusHeadEngine(cfg, op)
+        feats, rois, obj = pack_views(views)
+        vb = ViewBatch([f.cuda() for f in feats], [r.cuda() for r in rois], obj.cuda(), R)
+        out = eng.train_step(vb, torch.unique(case["gt_classes"]).cuda())
+        torch.cuda.synchronize()
+        # labels: the oracle without any override IS the reference (pinned on the CPU); the device must agree
+        _, aux = ref.train_step(views, case["gt_classes"], p, C, K)
+        for k in range(K):
+            b = aux["branches"][k]
+            assert torch.equal(out.aux["gt_class"][k].cpu().long(), b["gt_classes"]), (name, k)
+            assert torch.equal(out.aux["gt_index"][k].cpu().long(), b["gt_index"]), (name, k)
+        for key, v in exp["losses"].items():
+            assert abs(out.losses[key].item() - float(v)) < 1e-3, (name, key, out.losses[key].item(), float(v))
+        emap = sg.engine_key_map(K)
+        errs = {}
+        for rname, ekey in emap.items():
+            e = exp["grads"][rname]
+            got = out.grads[ekey].cpu().float()
+            if ekey == "det_b":
+                assert got.abs().max().item() < 1e-3 * max(exp["grads"]["box_predictor.cls.bias"].abs().max().item(), 1e-6) + 1e-7
+                continue
+            errs[ekey] = _rel_err(got, e)
+        errs["feat1"] = _rel_err(out.grad_feats[0].cpu(), exp["grad_feat1"])
+        errs["feat2"] = _rel_err(out.grad_feats[1].cpu(), exp["grad_feat2"])
+        print(name, "relative Frobenius gradient errors vs the reference:", {k: round(v, 4) for k, v in errs.items()})
+        assert max(errs.values()) < 3e-2, (name, errs)
+
+
+@pytest.mark.parametrize("C,K,R", [(20, 3, 2000), (80, 3, 2000), (20, 4, 2000)])
+def test_whole_step_at_the_bench_shape(cuda_lib, C, K, R):
+    """ONE whole step at BASELINE's full shape (4 views 480x640 + 576x768, 2000 proposals, 512 channels, fc 4096, dropout
+    0.5 with the kernel's own keep-masks) on the exact tensors bench.py feeds (synthetic.training_image(0), seed 1434):
+    engine vs oracle.train_step.  Losses 1e-3, scores 1e-2, labels / weights / indices bit-exact given the device's
+    view-averaged scores; gradient errors are printed per tensor.  VOC (configs[1]), COCO (configs[3]), shipped K=4."""
+    from sos_wsod_b200 import ops
+    from sos_wsod_b200.engine import HeadConfig, HeadOperands, OICRPlusHeadEngine, ViewBatch
+    from sos_wsod_b200.synthetic import pack_views, training_image
+
+    V = 4
+    sviews, gt = training_image(0, 0, R=R, num_classes=C, cfg_id=2)
+    views = [ref.View(feat=v.feat, boxes=v.boxes, obj=v.obj, image_size=v.image_size) for v in sviews]
+    g = torch.Generator().manual_seed(1234)
+    p = ref.init_head_params(C, K, generator=g)
+    for t in (p.cls_w, p.det_w):
+        t.mul_(3.0)
+    for r in p.refine:
+        r[0].mul_(20.0)
+        r[2].mul_(20.0)
+    cfg = HeadConfig(num_classes=C, refine_k=K, dropout_p=0.5)
+    op = HeadOperands(cfg, *[t.cuda() for t in (p.fc1_w, p.fc1_b, p.fc2_w, p.fc2_b, p.cls_w, p.cls_b, p.det_w, p.det_b)],
+                      [tuple(t.cuda() for t in r) for r in p.refine])
+    eng = OICRPlusHeadEngine(cfg, op)
+    feats, rois, obj = pack_views(sviews)
+    vb = ViewBatch([f.cuda() for f in feats], [r.cuda() for r in rois], obj.cuda(), R)
+    seeds = (101, 202)
+    out = eng.train_step(vb, gt.cuda(), dropout_seeds=seeds)
+    torch.cuda.synchronize()
+    m1 = ops.dropout_mask(V * R, cfg.fc_dim, 0.5, seeds[0]).cpu().float()
+    m2 = ops.dropout_mask(V * R, cfg.fc_dim, 0.5, seeds[1]).cpu().float()
+    drop_masks = [(m1[v * R:(v + 1) * R], m2[v * R:(v + 1) * R]) for v in range(V)]
+    p.requires_grad_(True)
+    for v in views:
+        v.feat.requires_grad_(True)
+    prev_dev = out.aux["prev"].cpu()
+    prev_override = [prev_dev[0][:, :C]] + [prev_dev[k] for k in range(1, K)]
+    exp_losses, aux = ref.train_step(views, gt, p, C, K, drop_masks=drop_masks, prev_override=prev_override)
+    sum(exp_losses.values()).backward()
+    for k, v in exp_losses.items():
+        assert abs(out.losses[k].item() - v.item()) < 1e-3, (k, out.losses[k].item(), v.item())
+    for vi in range(V):
+        assert _rel_err(out.aux["scores"][vi].cpu(), aux["wsddn_scores"][vi]) < 1e-2
+    for k in range(K - 1):
+        assert _rel_err(prev_dev[k + 1], aux["branches"][k]["next_prev"]) < 1e-2
+    for k in range(K):
+        b = aux["branches"][k]
+        M = int(out.aux["seed_count"][k].item())
+        assert torch.equal(out.aux["seed_index"][k, :M].cpu().long(), b["seeds"].index)
+        assert torch.equal(out.aux["gt_class"][k].cpu().long(), b["gt_classes"])
+        assert torch.equal(out.aux["gt_index"][k].cpu().long(), b["gt_index"])
+        assert torch.equal(out.aux["gt_weight"][k].cpu(), b["gt_weights"])
+    exp_g = {"fc1_w": p.fc1_w.grad, "fc1_b": p.fc1_b.grad, "fc2_w": p.fc2_w.grad, "fc2_b": p.fc2_b.grad,
+             "cls_w": p.cls_w.grad, "cls_b": p.cls_b.grad, "det_w": p.det_w.grad}
+    for k in range(K):
+        exp_g.update({f"r{k}_cls_w": p.refine[k][0].grad, f"r{k}_cls_b": p.refine[k][1].grad,
+                      f"r{k}_box_w": p.refine[k][2].grad, f"r{k}_box_b": p.refine[k][3].grad})
+    errs = {n: _rel_err(out.grads[n].cpu().float(), e) for n, e in exp_g.items()}
+    errs["feat1"] = _rel_err(out.grad_feats[0].cpu(), torch.cat([views[0].feat.grad, views[1].feat.grad], 0))
+    errs["feat2"] = _rel_err(out.grad_feats[1].cpu(), torch.cat([views[2].feat.grad, views[3].feat.grad], 0))
+    print(f"bench-shape step C={C} K={K}: losses", {k: round(v.item(), 5) for k, v in out.losses.items()},
+          "gradient rel. errors", {k: round(v, 4) for k, v in errs.items()})
+    assert max(errs.values()) < 5e-2, errs
+
+
+def test_reference_metric_scalars(cuda_lib):
+    """OICRPlusHeads.metric_scalars(): the reference's EventStorage names and values (roi_heads.py:364-373,
+    fast_rcnn_oicr.py:228-256), checked against the oracle's counters on the engine's own logits."""
+    from sos_wsod_b200.config import get_cfg
+    from sos_wsod_b200.modeling import build_roi_heads
+    from sos_wsod_b200.structures import Boxes, Instances, ShapeSpec
+
+    torch.manual_seed(0)
+    cfg = get_cfg()
+    cfg.MODEL.ROI_BOX_HEAD.DAN_DIM = [256, 256]
+    ch, R, C, K = 32, 200, 20, cfg.WSL.REFINE_NUM
+    heads = build_roi_heads(cfg, {"plain5": ShapeSpec(channels=ch, stride=8)}).cuda().train()
+    for r in heads.box_refinery:
+        r.cls_score.weight.data.mul_(20.0)
+    g = torch.Generator().manual_seed(3)
+    views = ref.synth_views(R, [(240, 320), (288, 384)], g, channels=ch)
+    f1 = torch.cat([views[0].feat, views[1].feat], 0).cuda()
+    f2 = torch.cat([views[2].feat, views[3].feat], 0).cuda()
+    props = [[Instances(v.image_size, proposal_boxes=Boxes(v.boxes.cuda()), objectness_logits=v.obj.cuda())] for v in views]
+    targets = [Instances(views[0].image_size, gt_classes=torch.tensor([2, 9, 9]).cuda(), gt_boxes=Boxes(torch.zeros(3, 4).cuda()))]
+    heads(None, [{"plain5": f1}, {"plain5": f2}], props, [targets, None, None, None])
+    got = heads.metric_scalars()
+    out = heads.engine().last_output
+    L = out.aux["logits"].cpu()
+    hc = heads.head_config()
+    for k in range(K):
+        y = out.aux["gt_class"][k].cpu().long()
+        assert got[f"roi_head/num_fg_samples_r{k}"] == float(((y >= 0) & (y < C)).sum())
+        assert got[f"roi_head/num_bg_samples_r{k}"] == float((y == C).sum())
+        assert got[f"roi_head/num_ig_samples_r{k}"] == float((y == -1).sum())
+        c0 = hc.col_ref0 + k * hc.ref_stride
+        z_view2 = L[2 * R:3 * R, c0:c0 + C + 1]          # the last `_log_accuracy` call sees view 2's logits (:381)
+        e = ref.reference_accuracy_scalars(z_view2, y, C)
+        for key, val in e.items():
+            assert abs(got[f"fast_rcnn/{key}_r{k}"] - val) < 1e-9, (key, k)
+        assert ("fast_rcnn/fg_cls_accuracy_r%d" % k in got) == ("fg_cls_accuracy" in e)
+
+    class _Store(dict):
+        def put_scalar(self, k, v):
+            self[k] = v
+
+    st = _Store()
+    heads.log_metrics(st)
+    assert st == got

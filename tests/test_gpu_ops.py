@@ -411,8 +411,11 @@ def test_wsddn_forward_backward(ops, R, C, V):
 # (4) OICR: mining + labelling (bit-exact), loss
 # ------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("R,C,G,K,seed", [(2000, 20, 3, 3, 0), (2000, 20, 1, 4, 1), (1500, 80, 7, 3, 2), (50, 20, 2, 1, 3),
-                                          (4000, 20, 4, 3, 4)])
+                                          (4000, 20, 4, 3, 4), (4000, 20, 4, 4, 5), (10000, 80, 8, 3, 6),
+                                          (10000, 80, 2, 4, 7), (16384, 80, 1, 1, 8)])
 def test_oicr_mine_label_bit_exact(ops, R, C, G, K, seed):
+    """Shipped shapes included: K=4 (voc07_oicr_plus.yaml:56-58), R=4000 (PRECOMPUTED_PROPOSAL_TOPK_TRAIN of
+    Base-RCNN-DilatedC5.yaml:4-10), R=10000 x C=80 (coco_oicr_plus.yaml:64-72), and the kernel's limit R=16384."""
     g = _gen(100 + seed)
     boxes = ref.synth_boxes(R, 480, 640, g)
     gt_int = torch.sort(torch.randperm(C, generator=g)[:G]).values

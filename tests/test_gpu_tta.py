@@ -225,12 +225,13 @@ def test_tta_wrapper_drop_in(ops):
     torch.testing.assert_close(fp, mp, rtol=1e-2, atol=1e-5)
     assert len(out_f) == len(out_p) or abs(len(out_f) - len(out_p)) <= 2
 
-    # a degenerate proposal is dropped by every view alike -> handled (the reference drops the row in each view)
+    # a degenerate proposal among the first top-k rows: the reference filters FIRST and then takes the first 150 survivors
+    # (test_time_augmentation_avg.py:62-71), i.e. it back-fills with row 150 of the 180 loaded proposals
     boxes2 = boxes.clone()
     boxes2[7] = torch.tensor([40.0, 30.0, 40.0, 90.0])
     dd2 = dict(dd, proposals=Instances((H, W), proposal_boxes=Boxes(boxes2), objectness_logits=obj))
     out2 = fused([dd2])[0]["instances"]
-    keep_rows = torch.tensor([i for i in range(150) if i != 7])
-    dd3 = dict(dd, proposals=Instances((H, W), proposal_boxes=Boxes(boxes2[:150][keep_rows]), objectness_logits=obj[:150][keep_rows]))
+    keep_rows = torch.tensor([i for i in range(151) if i != 7])
+    dd3 = dict(dd, proposals=Instances((H, W), proposal_boxes=Boxes(boxes2[keep_rows]), objectness_logits=obj[keep_rows]))
     out3 = fused([dd3])[0]["instances"]
     assert torch.equal(out2.scores, out3.scores) and torch.equal(out2.pred_boxes.tensor, out3.pred_boxes.tensor)

@@ -108,6 +108,46 @@ def test_plugin_surface_names_match_reference():
     heads2.load_state_dict(sd)
 
 
+def test_default_config_is_the_released_k4_and_loads_a_released_state_dict():
+    """every code_release yaml ships WSL.REFINE_NUM: 4 (voc07_oicr_plus.yaml:56-58); the DEFAULT config and
+    HeadConfig must build box_refinery_0..3 so that a released checkpoint loads strictly."""
+    from sos_wsod_b200.config import get_cfg
+    from sos_wsod_b200.engine import HeadConfig
+    from sos_wsod_b200.modeling import build_roi_heads
+    from sos_wsod_b200.structures import ShapeSpec
+
+    cfg = get_cfg()
+    assert cfg.WSL.REFINE_NUM == 4 and HeadConfig().refine_k == 4
+    cfg.MODEL.ROI_BOX_HEAD.DAN_DIM = [32, 32]
+    heads = build_roi_heads(cfg, {"plain5": ShapeSpec(channels=4, stride=8)})
+    released = {"box_head.fc1.weight": (32, 196), "box_head.fc1.bias": (32,), "box_head.fc2.weight": (32, 32),
+                "box_head.fc2.bias": (32,), "box_predictor.cls.weight": (20, 32), "box_predictor.cls.bias": (20,),
+                "box_predictor.det.weight": (20, 32), "box_predictor.det.bias": (20,)}
+    for k in range(4):
+        released.update({f"box_refinery_{k}.cls_score.weight": (21, 32), f"box_refinery_{k}.cls_score.bias": (21,),
+                         f"box_refinery_{k}.bbox_pred.weight": (80, 32), f"box_refinery_{k}.bbox_pred.bias": (80,)})
+    heads.load_state_dict({k: torch.zeros(v) for k, v in released.items()}, strict=True)
+
+
+@pytest.mark.parametrize("key,val", [("OICRPLUS.BBOX_UPDATE", True), ("MODEL.ROI_BOX_HEAD.BBOX_REG_LOSS_TYPE", "giou"),
+                                     ("MODEL.ROI_BOX_HEAD.SMOOTH_L1_BETA", 0.5), ("WSL.MEAN_LOSS", False),
+                                     ("MODEL.ROI_HEADS.IOU_LABELS", [0, 1, 1]), ("MODEL.ROI_HEADS.PROPOSAL_APPEND_GT", True),
+                                     ("MODEL.ROI_BOX_HEAD.CLS_AGNOSTIC_BBOX_REG", True), ("WSL.MIST_TYPE", "wetectron"),
+                                     ("WSL.REFINE_REG", [True, False, True, True]), ("MODEL.ROI_BOX_HEAD.BBOX_REG_LOSS_WEIGHT", 2.0)])
+def test_config_flags_that_change_the_maths_are_refused_at_construction(key, val):
+    """a flag the fused path does not implement must raise in from_config, never train silently with the
+    released configuration's arithmetic."""
+    from sos_wsod_b200.config import get_cfg
+    from sos_wsod_b200.modeling import build_roi_heads
+    from sos_wsod_b200.structures import ShapeSpec
+
+    cfg = get_cfg()
+    cfg.MODEL.ROI_BOX_HEAD.DAN_DIM = [32, 32]
+    cfg.merge_from_list([key, val])
+    with pytest.raises(NotImplementedError):
+        build_roi_heads(cfg, {"plain5": ShapeSpec(channels=4, stride=8)})
+
+
 def test_get_image_level_gt_and_structures():
     from sos_wsod_b200.modeling import convert_boxes_to_pooler_format, get_image_level_gt
     from sos_wsod_b200.structures import Boxes, Instances
@@ -126,22 +166,68 @@ _DIST_SCRIPT = r'''
 import os, sys, torch, torch.distributed as dist
 sys.path.insert(0, sys.argv[1])
 dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%s" % sys.argv[2], rank=int(sys.argv[3]), world_size=2)
-rank = dist.get_rank()
-# the bench / trainer hook: start an async averaging all-reduce per layer as soon as its gradients exist
-works = []
-def grad_hook(name, tensors):
-    for t in tensors:
-        t.div_(dist.get_world_size())          # gloo has no AVG; NCCL path uses ReduceOp.AVG
-        works.append(dist.all_reduce(t, op=dist.ReduceOp.SUM, async_op=True))
-g = {"head": [torch.full((4, 3), float(rank + 1)), torch.full((4,), float(10 * (rank + 1)))],
-     "fc1": [torch.arange(6.0).reshape(2, 3) * (rank + 1)]}
-for name, ts in g.items():
-    grad_hook(name, ts)
-for w in works:
-    w.wait()
-assert torch.allclose(g["head"][0], torch.full((4, 3), 1.5)), g["head"][0]
-assert torch.allclose(g["head"][1], torch.full((4,), 15.0))
-assert torch.allclose(g["fc1"][0], torch.arange(6.0).reshape(2, 3) * 1.5)
+rank, world = dist.get_rank(), 2
+from sos_wsod_b200.distributed import GradientExchange
+
+# ---- the host logic of both exchange modes against plain DDP arithmetic (SGD + momentum, two steps) ----
+torch.manual_seed(0)                       # same initial parameters on both ranks
+rows, cols, panels = 16, 6, 2
+init = {"fc1_w": torch.randn(rows, cols), "fc1_b": torch.randn(rows), "fc2_w": torch.randn(8, 8), "fc2_b": torch.randn(8),
+        "head_w": torch.randn(4, 8), "head_b": torch.randn(4)}
+lr, mom = 0.1, 0.9
+def local_grads(step, r):
+    g = torch.Generator().manual_seed(100 * step + r)
+    return {k: torch.randn(v.shape, generator=g) for k, v in init.items()}
+# DDP reference: every rank averages every gradient and updates everything
+ref_p = {k: v.clone() for k, v in init.items()}
+ref_b = {k: torch.zeros_like(v) for k, v in init.items()}
+for step in range(2):
+    gs = [local_grads(step, r) for r in range(world)]
+    for k in ref_p:
+        g = (gs[0][k] + gs[1][k]) / world
+        ref_b[k] = mom * ref_b[k] + g
+        ref_p[k] = ref_p[k] - lr * ref_b[k]
+for mode in ("allreduce", "sharded"):
+    master = {k: v.clone() for k, v in init.items()}
+    bufs = {k: torch.zeros_like(v) for k, v in init.items()}
+    opnd = {"fc1_w": master["fc1_w"].to(torch.bfloat16), "fc2_w": master["fc2_w"].to(torch.bfloat16)}
+    ex = GradientExchange(master, mode=mode, min_shard_elems=1)
+    assert ex.sharded == ({"fc1_w", "fc2_w"} if mode == "sharded" else set())
+    for step in range(2):
+        g = local_grads(step, rank)
+        ex.begin_step()
+        # the engine's hook order: head, fc2, fc1 in row panels, fc1 bias
+        ex.hook("head_w", g["head_w"], 0); ex.hook("head_b", g["head_b"], 0)
+        ex.hook("fc2_w", g["fc2_w"], 0); ex.hook("fc2_b", g["fc2_b"], 0)
+        per = rows // panels
+        for pi in range(panels):
+            ex.hook("fc1_w", g["fc1_w"][pi * per:(pi + 1) * per], pi * per)
+        ex.hook("fc1_b", g["fc1_b"], 0)
+        ex.wait_gradients()
+        for k in master:                   # the optimizer: only the owned rows of a sharded tensor
+            for lo, hi in ex.owned_rows(k):
+                bufs[k][lo:hi] = mom * bufs[k][lo:hi] + g[k][lo:hi]
+                master[k][lo:hi] -= lr * bufs[k][lo:hi]
+                if k in opnd:
+                    opnd[k][lo:hi] = master[k][lo:hi].to(torch.bfloat16)
+        ex.gather_operands(opnd)
+        ex.operand_gate()
+    if mode == "sharded":
+        own = ex._panel_ranges("fc1_w")
+        assert own == [(0, 8), (8, 16)], own
+        assert ex.master_stale
+        lo, hi = 4 * (1 - rank), 4 * (1 - rank) + 4          # rows of panel 0 owned by the OTHER rank: stale master
+        assert not torch.allclose(master["fc1_w"][lo:hi], ref_p["fc1_w"][lo:hi])
+        assert ex.bytes_last_step["reduce_scatter"] == (rows * cols + 64) * 4 and ex.bytes_last_step["all_gather"] == (rows * cols + 64) * 2
+    # the bf16 operands every rank computes with equal DDP's result on EVERY row, in both modes
+    for k in opnd:
+        assert torch.equal(opnd[k], ref_p[k].to(torch.bfloat16)), (mode, k)
+    ex.sync_master()
+    for k in master:
+        assert torch.allclose(master[k], ref_p[k], rtol=1e-6, atol=1e-7), (mode, k)
+    if mode == "sharded":
+        ex.gather_rows(bufs["fc1_w"], "fc1_w")
+        assert torch.allclose(bufs["fc1_w"], ref_b["fc1_w"], rtol=1e-6, atol=1e-7)
 # image sharding of detection-result generation: contiguous blocks, no collective (InferenceSampler)
 n = 11
 per = (n + 1) // 2

@@ -270,3 +270,62 @@ def test_tta_scalar_c_restatement_matches_reference_fixtures(tta_gold):
     out, keep = ref_kernels.tta_transform_proposals(b, (60, 80), (120, 160), True)
     eo, ek = ref.tta_transform_proposals(torch.from_numpy(b), (60, 80), (120, 160), True)
     assert np.array_equal(out, eo.numpy()) and keep.tolist() == ek.tolist() == [True, False, False]
+
+
+# ---------------------------------------------------------------- (d) one WHOLE step of the reference's own OICRPlusHeads.forward
+@pytest.mark.parametrize("name", ["voc_k3", "coco_k4"])
+@pytest.mark.parametrize("mode", ["eval_dropout", "train_dropout"])
+def test_train_step_vs_reference_forward_box(name, mode):
+    """oracle.train_step against tests/golden/step_golden.pt: losses, parameter gradients and conv5 gradients of
+    `OICRPlusHeads.forward` + backward run from the reference's own class (roi_heads_oicrplus.py:149-430) -- pins the
+    view averaging (:290-294, :390-395), the /4.0 combines (:288, :384-388) and the `2_flip` quirk (:381)."""
+    import step_golden_util as sg
+
+    case = sg.load()[name]
+    exp = case[mode]
+    p = sg.head_params(case).requires_grad_(True)
+    vs = sg.views(case)
+    for v in vs:
+        v.feat.requires_grad_(True)
+    masks = None
+    if mode == "train_dropout":
+        masks = [(a.float(), b.float()) for a, b in exp["drop_masks"]]
+    losses, aux = ref.train_step(vs, case["gt_classes"], p, case["C"], case["K"], drop_masks=masks)
+    assert set(losses) == set(exp["losses"])
+    for k, v in exp["losses"].items():
+        assert abs(float(losses[k]) - float(v)) <= 1e-6 * max(1.0, abs(float(v))), (k, float(losses[k]), float(v))
+    sum(losses.values()).backward()
+    for n, t in zip(sg.grad_key_map(case["K"]), p.tensors()):
+        e = exp["grads"][n]
+        assert torch.allclose(t.grad, e, rtol=1e-4, atol=1e-7 + 1e-5 * float(e.abs().max())), (n, float((t.grad - e).abs().max()))
+    g1 = torch.cat([vs[0].feat.grad, vs[1].feat.grad], 0)
+    g2 = torch.cat([vs[2].feat.grad, vs[3].feat.grad], 0)
+    for got, e in ((g1, exp["grad_feat1"]), (g2, exp["grad_feat2"])):
+        assert torch.allclose(got, e, rtol=1e-4, atol=1e-7 + 1e-5 * float(e.abs().max()))
+    # without the quirk the step must differ (the fixture really exercises :381)
+    l2, _ = ref.train_step(sg.views(case), case["gt_classes"], sg.head_params(case), case["C"], case["K"], drop_masks=masks,
+                           reproduce_flip_quirk=False)
+    assert any(abs(float(l2[k]) - float(exp["losses"][k])) > 1e-7 for k in l2 if k != "loss_cls")
+
+
+def test_reference_metric_scalars():
+    """The EventStorage scalars the reference's step logs (names + values of the last view written):
+    roi_head/num_{fg,bg,ig}_samples_r{k} (roi_heads.py:364-373) and fast_rcnn/{cls_accuracy,fg_cls_accuracy,
+    false_negative}_r{k} (fast_rcnn_oicr.py:228-256) -- the oracle's counters reproduce them."""
+    import step_golden_util as sg
+
+    case = sg.load()["voc_k3"]
+    exp = case["eval_dropout"]["storage"]
+    vs = sg.views(case)
+    losses, aux = ref.train_step(vs, case["gt_classes"], sg.head_params(case), case["C"], case["K"])
+    C = case["C"]
+    for k, br in enumerate(aux["branches"]):
+        y = br["gt_classes"]
+        assert exp[f"roi_head/num_fg_samples_r{k}"] == float(((y >= 0) & (y < C)).sum())
+        assert exp[f"roi_head/num_bg_samples_r{k}"] == float((y == C).sum())
+        assert exp[f"roi_head/num_ig_samples_r{k}"] == float((y == -1).sum())
+        # _log_accuracy is called per view; the storage keeps the LAST call = view 2_flip, which (quirk) uses view 2's logits
+        m = ref.reference_accuracy_scalars(br["logits"][2], y, C)
+        for key in ("cls_accuracy", "fg_cls_accuracy", "false_negative"):
+            if f"fast_rcnn/{key}_r{k}" in exp:
+                assert abs(exp[f"fast_rcnn/{key}_r{k}"] - m[key]) < 1e-6, (key, k, exp[f"fast_rcnn/{key}_r{k}"], m[key])
