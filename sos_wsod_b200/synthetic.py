@@ -1,7 +1,7 @@
 """Seeded synthetic inputs of the hot path: the proposal boxes, conv5 maps and objectness scores that
-bench.py, smoke() and the examples feed to the head.  Plain torch on the CPU, no oracle and no CUDA involved; the
-parity tests check that this generator and the oracle's own (oracle/oicr_plus_ref.py:synth_views, which the committed
-golden fixtures were made with) produce identical tensors for the same seed."""
+bench.py and the examples feed to the head.  Plain torch on the CPU, nothing of the test infrastructure and no CUDA
+involved; the parity tests check that this generator and the test suite's own (the one the committed golden fixtures
+were made with) produce identical tensors for the same seed."""
 from __future__ import annotations
 
 from dataclasses import dataclass

@@ -1,5 +1,5 @@
 """The committed fixtures are what the REFERENCE'S OWN CODE produces: where /root/reference is mounted (the build
-container; never the GPU box) the three generators under tests/golden/ are re-run into a scratch directory and must
+container; never the GPU box) the generators under tests/golden/ are re-run into a scratch directory and must
 reproduce the committed files value for value.  Skipped elsewhere."""
 import json
 import os
@@ -26,7 +26,7 @@ def _same(x, y):
 
 
 @pytest.mark.parametrize("script,artefact", [("make_golden.py", "oicr_plus_golden.pt"), ("make_golden_eval.py", "eval_golden.json"),
-                                             ("make_golden_tta.py", "tta_golden.pt")])
+                                             ("make_golden_tta.py", "tta_golden.pt"), ("make_golden_step.py", "step_golden.pt")])
 def test_generators_reproduce_the_committed_fixtures(tmp_path, script, artefact):
     env = dict(os.environ, SOSWSOD_GOLDEN_OUT=str(tmp_path))
     r = subprocess.run([sys.executable, os.path.join(GOLD, script)], capture_output=True, text=True, env=env, timeout=600)

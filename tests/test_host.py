@@ -148,6 +148,25 @@ def test_config_flags_that_change_the_maths_are_refused_at_construction(key, val
         build_roi_heads(cfg, {"plain5": ShapeSpec(channels=4, stride=8)})
 
 
+def test_synthetic_inputs_equal_the_fixture_generator():
+    """sos_wsod_b200.synthetic (what bench.py feeds) and the test suite's generator (what the golden fixtures were made
+    with) are independent implementations of SURVEY.md §8d: identical tensors for the same seed."""
+    from oracle import oicr_plus_ref as ref
+    from sos_wsod_b200 import synthetic as syn
+
+    for seed, R, sizes, ch in [(1434, 2000, [(480, 640), (576, 768)], 4), (7, 200, [(240, 320), (288, 384)], 8)]:
+        a = ref.synth_views(R, sizes, torch.Generator().manual_seed(seed), channels=ch)
+        b = syn.synth_views(R, sizes, torch.Generator().manual_seed(seed), channels=ch)
+        for x, y in zip(a, b):
+            assert torch.equal(x.feat, y.feat) and torch.equal(x.boxes, y.boxes) and torch.equal(x.obj, y.obj)
+            assert tuple(x.image_size) == tuple(y.image_size)
+    views, gt = syn.training_image(0, 0, R=300, channels=4)
+    assert len(views) == 4 and 1 <= gt.numel() <= 4 and bool((gt[1:] > gt[:-1]).all())
+    feats, rois, obj = syn.pack_views(views)
+    assert feats[0].shape[0] == 2 and rois[0].shape == (600, 5) and obj.shape == (1200,)
+    assert rois[0][:300, 0].eq(0).all() and rois[0][300:, 0].eq(1).all()
+
+
 def test_get_image_level_gt_and_structures():
     from sos_wsod_b200.modeling import convert_boxes_to_pooler_format, get_image_level_gt
     from sos_wsod_b200.structures import Boxes, Instances
