@@ -357,6 +357,7 @@ class OICRPlusHeadEngine:
                 self.launches_last_step += 1
         if side is not None:
             torch.cuda.current_stream().wait_stream(side)
+        if grad_hook is None:
             dbh = dbh_raw * col_scale
         grads = {"fc1_w": dW6, "fc1_b": db6, "fc2_w": dW7, "fc2_b": db7}
         for wk, bk, r0, n in op.head_slices():

@@ -603,3 +603,38 @@ def test_detect_matches_reference_inference(ops, R, C, thr):
     assert torch.equal(dc[:n].cpu().long(), ec)
     assert torch.equal(ds[:n].cpu(), es)
     assert torch.equal(db[:n].cpu(), eb)
+
+
+def test_roi_pool_backward_duplicate_argmax_merge(ops):
+    """The queued backward merges, per roi and plane, the bins that share an arg-max cell (up to 2 x 2 neighbouring
+    bins) before accumulating.  Sparse peaky planes make such groups the rule: every bin around a peak points at it.
+    Checked against torchvision's autograd and for run-to-run identity; with the merge switched off the same kernel must
+    give the same gradients up to fp32 summation order."""
+    import torchvision
+
+    g = _gen(977)
+    N, C, h, w = 2, 64, 60, 80
+    feat = torch.zeros((N, C, h, w))
+    idx = torch.randint(0, h * w, (N, C, 60), generator=g)
+    feat.view(N, C, -1).scatter_(2, idx, torch.rand((N, C, 60), generator=g) + 0.5)      # ~1 % of the cells are peaks
+    feat[:, 5] = 0.0                                                                      # an all-zero plane (first-cell arg-max)
+    feat[:, 6] = 1.0                                                                      # a constant plane
+    feat.requires_grad_(True)
+    rois = ref.boxes_to_pooler_format([ref.synth_boxes(600, h * 8, w * 8, g) for _ in range(N)])
+    obj = torch.rand(rois.size(0), generator=g)
+    pooled = torchvision.ops.roi_pool(feat, rois, (7, 7), 0.125) * (obj + 1).view(-1, 1, 1, 1)
+    go = torch.randn(pooled.shape, generator=g).to(torch.bfloat16).float()
+    pooled.backward(go)
+    plan = ops.roi_pool_plan(rois.cuda(), (N, C, h, w), row_scale=obj.cuda(), row_scale_bias=1.0)
+    _, arg, _ = ops.roi_pool_forward(feat.detach().cuda(), rois.cuda(), want_f32=False, argmax_u16=True, want_bf16=True,
+                                     row_scale=obj.cuda(), row_scale_bias=1.0, plan=plan)
+    a = arg.view(torch.int16).cpu().view(-1, C, 49)
+    dup = (a[:, :, :-1] == a[:, :, 1:]) & (a[:, :, 1:] != -1)
+    assert dup.float().mean() > 0.05, "the fixture must contain many bins sharing a cell"
+    go_dev = go.flatten(1).cuda().to(torch.bfloat16)
+    gf = ops.roi_pool_backward(go_dev, arg, rois.cuda(), (N, C, h, w), row_scale=obj.cuda(), row_scale_bias=1.0, plan=plan)
+    torch.testing.assert_close(gf.cpu(), feat.grad, rtol=1e-4, atol=2e-4)
+    gf2 = ops.roi_pool_backward(go_dev, arg, rois.cuda(), (N, C, h, w), row_scale=obj.cuda(), row_scale_bias=1.0, plan=plan)
+    assert torch.equal(gf, gf2)
+    general = ops.roi_pool_backward(go_dev, arg, rois.cuda(), (N, C, h, w), row_scale=obj.cuda(), row_scale_bias=1.0)
+    torch.testing.assert_close(gf, general, rtol=1e-4, atol=2e-4)
