@@ -781,13 +781,11 @@ constexpr int kBwdQSteps = 4;                       // colour steps per chunk / 
 constexpr int kBwdQSlotBytes = kBwdQSteps * 32 * 8;
 constexpr int kBwdQMaxP = 6;
 constexpr int kBwdQMaxQ = 8;
-constexpr uint32_t kBwdQFreeBit = 1u << 18;         // queue entry: the chunk's steps are independent (see the prep warps)
 
 struct BwdQCfg {
     BwdFastCfg b;
     int P;             // prep warps per plane pair
     int LQ;            // log2 of the queue depth Q (slots per plane pair)
-    int dedup;         // 1: prep warps merge a roi's bins that share an arg-max cell (bf16 gradients, h*w <= 0xFFF0)
 };
 
 struct __align__(16) BwdMetaQ {
@@ -966,23 +964,6 @@ roi_pool_bwd_q_kernel(const __grid_constant__ CUtensorMap tmap_arg, const __grid
             if (have_next) q_load(qbase + ((seq + 1u) & qmask) * kBwdQSlotBytes, nlo, nhi);
             const uint32_t ntag = 0x1000u | (((seq + 1u) >> LQ) & 0xFFFu);
             bool nvalid = false;
-            if (lo[kBwdQSteps - 1] & kBwdQFreeBit) {
-                // the prep warp merged the roi's duplicate cells: the chunk's 4 x 32 targets are pairwise distinct
-                // (idle lanes aim at their private dummy word), so the four read-add-writes are independent -- one
-                // shared-memory latency per roi instead of four
-                float v[kBwdQSteps];
-#pragma unroll
-                for (int i = 0; i < kBwdQSteps; ++i)
-                    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v[i]) : "r"(lo[i] & 0x3FFFFu) : "memory");
-                nvalid = __all_sync(FULL_MASK, have_next && (nlo[kBwdQSteps - 1] >> 19) == ntag);
-#pragma unroll
-                for (int i = 0; i < kBwdQSteps; ++i) {
-                    v[i] += __uint_as_float(hi[i]);
-                    asm volatile("st.shared.f32 [%0], %1;" ::"r"(lo[i] & 0x3FFFFu), "f"(v[i]) : "memory");
-                }
-                __syncwarp();
-                return nvalid;
-            }
 #pragma unroll
             for (int i = 0; i < kBwdQSteps; ++i) {
                 const uint32_t ad = lo[i] & 0x3FFFFu;
@@ -1063,85 +1044,19 @@ roi_pool_bwd_q_kernel(const __grid_constant__ CUtensorMap tmap_arg, const __grid
                     ad = ok ? my_s + 4u * rel : dummy_s;
                     vl = ok ? __float_as_uint(__uint_as_float(graw) * m.scale) : 0u;
                 };
-                auto publish = [&](const uint32_t (&ad)[kBwdQSteps], const uint32_t (&vl)[kBwdQSteps], uint32_t seq,
-                                   uint32_t flags = 0u) {
+                auto publish = [&](const uint32_t (&ad)[kBwdQSteps], const uint32_t (&vl)[kBwdQSteps], uint32_t seq) {
                     uint32_t consumed;
                     do {   // the slot's previous occupant is chunk seq - Q
                         asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(consumed) : "r"(cons_s) : "memory");
                     } while ((int)(seq - consumed) >= Q);
-                    const uint32_t hdr = ((0x1000u | ((seq >> LQ) & 0xFFFu)) << 19) | flags;
+                    const uint32_t hdr = (0x1000u | ((seq >> LQ) & 0xFFFu)) << 19;
                     const uint32_t qa = qpair + (seq & qmask) * kBwdQSlotBytes;
 #pragma unroll
                     for (int i = 0; i < kBwdQSteps; ++i)
                         asm volatile("st.volatile.shared.v2.u32 [%0], {%1, %2};" ::"r"(qa + 256u * i), "r"(ad[i] | hdr), "r"(vl[i]) : "memory");
                 };
                 uint32_t ad[kBwdQSteps], vl[kBwdQSteps];
-                if (sizeof(GradT) == 2 && qc.dedup && m.code == kCode22) {
-                    // strides 2 x 2 + duplicate merge.  Two bins of a roi can share their arg-max cell only when they
-                    // are neighbours (incl. diagonally: the bins holding a cell form a block of at most 2 x 2 bins).  The
-                    // FIRST bin of such a group in row-major order absorbs the gradients of the others -- every later
-                    // member is one of its four "later" neighbours (right, down-left, down, down-right) -- and the
-                    // others aim at the dummy word, so the roi's 49 updates of a plane hit pairwise distinct cells and
-                    // the accumulator runs them as ONE round of independent read-add-writes.
-                    // A lane holds the 2 x 2 bins (2la+i, 2lb+j); w[2i+j] = arg-max | bf16 gradient << 16.  Bins outside
-                    // the 7 x 7 grid and empty bins carry the codes 0xFFF0 + k, which never compare equal across any
-                    // neighbour relation (a relation always pairs different k) -- so shuffles that wrap around the
-                    // half-warp need no masking: they land on such codes.
-                    uint32_t w[4];
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        w[k] = 0xFFF0u | (uint32_t)k;
-                        if (v22[k]) {
-                            unsigned a, g;
-                            asm volatile("ld.shared.u16 %0, [%1];" : "=r"(a) : "r"(sa + 2u * (unsigned)(e22a[k] + rowe)));
-                            asm volatile("ld.shared.u16 %0, [%1];" : "=r"(g) : "r"(sg + 2u * (unsigned)(e22g[k] + rowe)));
-                            if (a != 0xFFFFu) w[k] = a | (g << 16);
-                        }
-                    }
-                    const uint32_t r00 = __shfl_sync(FULL_MASK, w[0], (lane + 1) & 31), r10 = __shfl_sync(FULL_MASK, w[2], (lane + 1) & 31);
-                    const uint32_t d00 = __shfl_sync(FULL_MASK, w[0], (lane + 4) & 31), d01 = __shfl_sync(FULL_MASK, w[1], (lane + 4) & 31);
-                    const uint32_t dr00 = __shfl_sync(FULL_MASK, w[0], (lane + 5) & 31);
-                    const uint32_t dl01 = __shfl_sync(FULL_MASK, w[1], (lane + 3) & 31);
-                    const uint32_t l01 = __shfl_sync(FULL_MASK, w[1], (lane + 31) & 31), l11 = __shfl_sync(FULL_MASK, w[3], (lane + 31) & 31);
-                    const uint32_t u10 = __shfl_sync(FULL_MASK, w[2], (lane + 28) & 31), u11 = __shfl_sync(FULL_MASK, w[3], (lane + 28) & 31);
-                    const uint32_t ul11 = __shfl_sync(FULL_MASK, w[3], (lane + 27) & 31);
-                    const uint32_t ur10 = __shfl_sync(FULL_MASK, w[2], (lane + 29) & 31);
-                    auto same = [](uint32_t a, uint32_t b) { return ((a ^ b) & 0xFFFFu) == 0u; };
-                    auto gr = [](uint32_t x) { return __uint_as_float(x & 0xFFFF0000u); };
-                    // absorb, in row-major order of the later neighbours: right, down-left, down, down-right
-                    float sum[4];
-                    sum[0] = gr(w[0]); sum[1] = gr(w[1]); sum[2] = gr(w[2]); sum[3] = gr(w[3]);
-                    if (same(w[0], w[1])) sum[0] += gr(w[1]);
-                    if (same(w[0], l11)) sum[0] += gr(l11);
-                    if (same(w[0], w[2])) sum[0] += gr(w[2]);
-                    if (same(w[0], w[3])) sum[0] += gr(w[3]);
-                    if (same(w[1], r00)) sum[1] += gr(r00);
-                    if (same(w[1], w[2])) sum[1] += gr(w[2]);
-                    if (same(w[1], w[3])) sum[1] += gr(w[3]);
-                    if (same(w[1], r10)) sum[1] += gr(r10);
-                    if (same(w[2], w[3])) sum[2] += gr(w[3]);
-                    if (same(w[2], dl01)) sum[2] += gr(dl01);
-                    if (same(w[2], d00)) sum[2] += gr(d00);
-                    if (same(w[2], d01)) sum[2] += gr(d01);
-                    if (same(w[3], r10)) sum[3] += gr(r10);
-                    if (same(w[3], d00)) sum[3] += gr(d00);
-                    if (same(w[3], d01)) sum[3] += gr(d01);
-                    if (same(w[3], dr00)) sum[3] += gr(dr00);
-                    // a bin with an earlier neighbour (left, up-left, up, up-right) on the same cell has been absorbed
-                    bool drop[4];
-                    drop[0] = same(w[0], l01) || same(w[0], ul11) || same(w[0], u10) || same(w[0], u11);
-                    drop[1] = same(w[1], w[0]) || same(w[1], u10) || same(w[1], u11) || same(w[1], ur10);
-                    drop[2] = same(w[2], l11) || same(w[2], l01) || same(w[2], w[0]) || same(w[2], w[1]);
-                    drop[3] = same(w[3], w[2]) || same(w[3], w[0]) || same(w[3], w[1]) || same(w[3], r00);
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const unsigned rel = (w[k] & 0xFFFFu) - (unsigned)band_lo;   // the 0xFFFx codes and other bands fail the test
-                        const bool ok = !drop[k] && rel < band_cells;
-                        ad[k] = ok ? my_s + 4u * rel : dummy_s;
-                        vl[k] = ok ? __float_as_uint(sum[k] * m.scale) : 0u;
-                    }
-                    publish(ad, vl, (uint32_t)m.cbase, kBwdQFreeBit);
-                } else if (m.code == kCode22) {
+                if (m.code == kCode22) {
                     // strides 2 x 2 (every roi at least 7 x 7 cells): one chunk, the lane's four bins at constant offsets
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
@@ -1252,7 +1167,6 @@ static bool pick_bwd_q_cfg(int n, int c, int h, int w, int grad_bytes, BwdQCfg* 
                             out->b.smem = fixed + (size_t)stages * stage;
                             out->P = P;
                             out->LQ = LQ;
-                            out->dedup = (grad_bytes == 2 && (long long)h * w <= 0xFFF0 && env_int("SOSWSOD_BWDQ_DEDUP", 1)) ? 1 : 0;
                         }
                         if (stages >= 3) break;
                     }

@@ -606,10 +606,9 @@ def test_detect_matches_reference_inference(ops, R, C, thr):
 
 
 def test_roi_pool_backward_duplicate_argmax_merge(ops):
-    """The queued backward merges, per roi and plane, the bins that share an arg-max cell (up to 2 x 2 neighbouring
-    bins) before accumulating.  Sparse peaky planes make such groups the rule: every bin around a peak points at it.
-    Checked against torchvision's autograd and for run-to-run identity; with the merge switched off the same kernel must
-    give the same gradients up to fp32 summation order."""
+    """Neighbouring bins of a roi (up to 2 x 2 of them) can share their arg-max cell; the backward's colour steps exist to
+    keep such updates ordered.  Sparse peaky planes make these groups the rule: every bin around a peak points at it.
+    Checked against torchvision's autograd, the general kernel, and for run-to-run identity."""
     import torchvision
 
     g = _gen(977)
