@@ -32,6 +32,19 @@ void set_error(const char* fmt, ...);
 
 #define SOSWSOD_CHECK_LAUNCH() SOSWSOD_CHECK_CUDA(cudaGetLastError())
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is sticky per (function, device): raise it only when a launch needs more
+// than any launch before it (`high_water` = one static int per call site / template instantiation), not on every launch.
+#define SOSWSOD_ENSURE_SMEM(kern, bytes)                                                                              \
+    do {                                                                                                              \
+        static int high_water_[16] = {0};                                                                             \
+        int dev_ = 0;                                                                                                 \
+        SOSWSOD_CHECK_CUDA(cudaGetDevice(&dev_));                                                                     \
+        if (dev_ < 0 || dev_ >= 16 || (int)(bytes) > high_water_[dev_]) {                                             \
+            SOSWSOD_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes))); \
+            if (dev_ >= 0 && dev_ < 16) high_water_[dev_] = (int)(bytes);                                             \
+        }                                                                                                             \
+    } while (0)
+
 constexpr unsigned FULL_MASK = 0xffffffffu;
 
 __device__ __forceinline__ float warp_max(float v) {

@@ -433,7 +433,7 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, void* d, lo
                        const GemmEpilogue& ep, unsigned int* sched, cudaStream_t st) {
     auto kern = gemm_bf16_kernel<BLOCK_N, A_MN, B_MN, OUT_BF16>;
     const int smem = gemm_smem_bytes(BLOCK_N);
-    SOSWSOD_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    SOSWSOD_ENSURE_SMEM(kern, smem);
     const int tiles = ((m + kBlockM - 1) / kBlockM) * ((n + BLOCK_N - 1) / BLOCK_N);
     const int grid = tiles < device_num_sms() ? tiles : device_num_sms();
     kern<<<grid, kGemmThreads, smem, st>>>(ta, tb, d, ldd, m, n, k, ep, sched);

@@ -374,7 +374,7 @@ static int run_nms_pipeline(const NmsSource& src, int lists, int n, float thr, i
     const int n_pow2 = next_pow2(n < 2 ? 2 : n);
     const int nb = (n + 63) / 64;
     const size_t smem = (size_t)n_pow2 * 8;
-    SOSWSOD_CHECK_CUDA(cudaFuncSetAttribute(nms_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SOSWSOD_ENSURE_SMEM(nms_sort_kernel, smem);
     nms_sort_kernel<<<lists, kSortThreads, smem, st>>>(src, n, n_pow2, w.sorted_idx, w.sorted_box, w.counts);
     SOSWSOD_CHECK_LAUNCH();
     nms_mask_kernel<<<dim3(nb, nb, lists), 64, 0, st>>>(w.sorted_box, w.counts, n, nb, thr, w.mask);
@@ -496,7 +496,7 @@ extern "C" int soswsod_detect(const float* probs, const float* pred_boxes, int R
     if (rc) return rc;
     const int n_pow2 = next_pow2(C * topk < 2 ? 2 : C * topk);
     const size_t smem = (size_t)n_pow2 * 8;
-    SOSWSOD_CHECK_CUDA(cudaFuncSetAttribute(detect_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SOSWSOD_ENSURE_SMEM(detect_topk_kernel, smem);
     detect_topk_kernel<<<1, kSortThreads, smem, st>>>(probs, pred_boxes, w.sorted_idx, w.kept_pos, w.kept_count, R, C,
                                                      topk, n_pow2, img_h, img_w, det_boxes, det_scores, det_classes,
                                                      det_rows, num_det);

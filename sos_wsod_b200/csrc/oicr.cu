@@ -538,7 +538,7 @@ extern "C" int soswsod_oicr_mine_label(const float* prev, long long ld_prev, con
     unsigned long long* cand_key = reinterpret_cast<unsigned long long*>(workspace);
     int32_t* cand_row = reinterpret_cast<int32_t*>(cand_key + (size_t)K * m0);
     const size_t smem = (size_t)n_pow2 * 8;
-    SOSWSOD_CHECK_CUDA(cudaFuncSetAttribute(oicr_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SOSWSOD_ENSURE_SMEM(oicr_topk_kernel, smem);
     oicr_topk_kernel<<<dim3(G, K), kOicrThreads, smem, st>>>(prev, ld_prev, gt_classes, G, gt_count, R, kt, score_thr,
                                                             n_pow2, cand_key, cand_row);
     SOSWSOD_CHECK_LAUNCH();

@@ -575,31 +575,6 @@ roi_pool_bwd_kernel(const __grid_constant__ CUtensorMap tmap_arg, const __grid_c
     }
 }
 
-// Fallback for planes that do not fit shared memory: zero + global atomics (documented, rarely used).
-template <typename GradT, typename ArgT>
-__global__ void roi_pool_bwd_atomic_kernel(const GradT* __restrict__ grad, long long ld_grad,
-                                           const ArgT* __restrict__ argmax, const float* __restrict__ rois,
-                                           long long total, const float* __restrict__ row_scale,
-                                           float row_scale_bias, int C, int H, int W, int PP,
-                                           float* __restrict__ grad_feat) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= total) return;
-    const int bin = (int)(i % PP);
-    const int c = (int)((i / PP) % C);
-    const int r = (int)(i / ((long long)PP * C));
-    const ArgT raw = argmax[i];
-    int a = (sizeof(ArgT) == 2) ? (((unsigned)raw == 0xFFFFu) ? -1 : (int)(unsigned)raw) : (int)raw;
-    if (a < 0) return;
-    float gv;
-    if (sizeof(GradT) == 2)
-        gv = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(&grad[(size_t)r * ld_grad + (size_t)c * PP + bin]));
-    else
-        gv = *reinterpret_cast<const float*>(&grad[(size_t)r * ld_grad + (size_t)c * PP + bin]);
-    const float s = row_scale ? __fadd_rn(row_scale[r], row_scale_bias) : 1.f;
-    const int b = (int)rois[(size_t)r * 5];
-    atomicAdd(grad_feat + ((size_t)b * C + c) * H * W + a, gv * s);
-}
-
 static int g_max_smem_optin = -1;
 static int g_num_sms = -1;
 static int query_device() {
@@ -645,7 +620,7 @@ static int launch_fwd(const float* feat, int n, int c, int h, int w, const float
     const int rois_per_cta = (R + chunks - 1) / chunks;
     chunks = (R + rois_per_cta - 1) / rois_per_cta;
     auto kern = roi_pool_fwd_kernel<CT, NT, COMPACT>;
-    SOSWSOD_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SOSWSOD_ENSURE_SMEM(kern, smem);
     kern<<<dim3(groups, chunks), NT, smem, st>>>(feat, c, h, w, rois, R, PH, PW, scale, row_scale, bias, out_f32, a32, a16,
                                                  obf, ld, plane_stride, rois_per_cta);
     SOSWSOD_CHECK_LAUNCH();
@@ -799,24 +774,21 @@ static int launch_bwd(const void* grad, long long ld_grad, const void* argmax, c
         const int threads = (cfg.CT + 1) * 32;
         if (PH == 7 && PW == 7) {
             auto kern = roi_pool_bwd_kernel<GradT, ArgT, 7, 7>;
-            SOSWSOD_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem));
+            SOSWSOD_ENSURE_SMEM(kern, cfg.smem);
             kern<<<grid, threads, cfg.smem, st>>>(ta, tg, rois, R, row_scale, bias, n, c, h, w, PH, PW, scale, grad_feat, cfg);
         } else {
             auto kern = roi_pool_bwd_kernel<GradT, ArgT, 0, 0>;
-            SOSWSOD_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem));
+            SOSWSOD_ENSURE_SMEM(kern, cfg.smem);
             kern<<<grid, threads, cfg.smem, st>>>(ta, tg, rois, R, row_scale, bias, n, c, h, w, PH, PW, scale, grad_feat, cfg);
         }
         SOSWSOD_CHECK_LAUNCH();
         return SOSWSOD_OK;
     }
-    // misaligned inputs: zero + global atomics (documented fallback; not used by the head engine)
-    SOSWSOD_CHECK_CUDA(cudaMemsetAsync(grad_feat, 0, (size_t)n * c * HW * 4, st));
-    const long long total = (long long)R * c * PP;
-    if (total == 0) return SOSWSOD_OK;
-    roi_pool_bwd_atomic_kernel<GradT, ArgT><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
-        (const GradT*)grad, ld_grad, (const ArgT*)argmax, rois, total, row_scale, bias, c, h, w, PP, grad_feat);
-    SOSWSOD_CHECK_LAUNCH();
-    return SOSWSOD_OK;
+    // There is no atomic path.  The TMA-fed kernels need 16-byte aligned rows (the Python shim pads the channel count
+    // of odd layouts, ops.roi_pool_backward) and a band of a plane must fit shared memory.
+    set_error("roi_pool_backward: unsupported layout (grad / arg-max rows must be 16-byte aligned: pad the channel count to a "
+              "multiple of 8; planes of %d x %d cells must fit shared memory in at most 64 row bands)", h, w);
+    return SOSWSOD_ERR_UNSUPPORTED;
 }
 
 extern "C" int soswsod_roi_pool_backward(const void* grad_out, int grad_dtype, long long ld_grad,

@@ -376,7 +376,7 @@ static int launch_fwd_fast_ci(const float* feat, int n, int c, int h, int w, int
         }
     }
     auto kern = roi_pool_fwd_fast_kernel<CI>;
-    SOSWSOD_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SOSWSOD_ENSURE_SMEM(kern, smem);
     kern<<<dim3(groups, chunks), kFastThreads, smem, st>>>(feat, c, h, w, pv.img_start, pv.order, pv.rec, a16, obf, ld,
                                                           cells_pad, chunks);
     SOSWSOD_CHECK_LAUNCH();
@@ -411,19 +411,15 @@ int launch_fwd_fast(const float* feat, int n, int c, int h, int w, int R, const 
 // backward
 // ------------------------------------------------------------------------------------------------
 // A CTA owns the gradient planes of CT consecutive channels of one image (optionally one band of rows of them) in
-// shared memory.  Consumer warp w is the ONLY writer of channels c0+2w and c0+2w+1: lanes 0-15 update the first
-// plane, lanes 16-31 the second, so there is no atomic and no cross-warp race, and the accumulation order is fixed
-// (deterministic).  A producer warp streams [RT rois x BW columns] tiles of arg-max and grad_out through a TMA ring
-// (cp.async.bulk.tensor + mbarriers) and publishes each roi's (scale, colour strides) from the plan.
+// shared memory; ONE accumulator warp is the only writer of a pair of planes (lanes 0-15 the first, lanes 16-31 the
+// second), so there is no atomic and no cross-warp race, and the accumulation order is fixed (deterministic).
 //
 // Conflict freedom inside a warp step comes from PROPOSAL-BIN OWNERSHIP: the arg-max of a bin lies inside the bin,
 // and two bins of one roi can only share a cell when their row ranges AND column ranges overlap.  The plan holds,
 // per roi, the smallest strides (mh, mw) such that bins mh rows (mw columns) apart are disjoint (2 x 2 for every roi
 // at least 7 cells high and wide, larger for tiny rois whose bins repeat cells).  A 16-lane half-warp = 4 x 4 blocks
 // of mh x mw bins; a step takes ONE colour (i, j) -- bin (la*mh + i, lb*mw + j) of every block -- whose bins are
-// pairwise disjoint, so every lane does a plain read-add-write on its own cell.  The operands of the next roi are
-// fetched while the (ordered) steps of the current one run, leaving the read-add-write chain on the plane as the
-// only dependency.
+// pairwise disjoint, so every lane does a plain read-add-write on its own cell.
 constexpr int kBwdFastMaxCT = 8;
 constexpr int kBwdFastMaxRT = 16;
 
@@ -432,335 +428,13 @@ struct BwdFastCfg {
     size_t smem;
 };
 
-struct BwdMeta {
-    float scale;
-    int code;   // 0 = skip (roi of another image); else 1 | mh << 8 | mw << 16
-};
-
-constexpr int kBwdKW = 4;        // warps sharing one pair of planes (they take the rois of a tile in turn)
-constexpr int kBwdMaxSteps = 9;  // colour steps prepared in registers at a time (3 x 3 strides; more are chunked)
-
-template <typename GradT>
-__global__ void __launch_bounds__((kBwdFastMaxCT / 2 * kBwdKW + 1) * 32, 1)
-roi_pool_bwd_fast_kernel(const __grid_constant__ CUtensorMap tmap_arg, const __grid_constant__ CUtensorMap tmap_grad,
-                         const int* __restrict__ img_start, const int* __restrict__ order,
-                         const RoiRecord* __restrict__ rec, int C, int H, int W, float* __restrict__ grad_feat,
-                         BwdFastCfg cfg) {
-    constexpr int PP = kPP;
-    constexpr int KW = kBwdKW;
-    extern __shared__ uint8_t smem_raw[];
-    const int CT = cfg.CT, BW = cfg.BW, nbox = cfg.nbox, S = cfg.stages, RT = cfg.RT;
-    const int NP = (CT + 1) >> 1;   // plane pairs
-    const int NCW = NP * KW;        // consumer warps
-    const uint32_t base = (smem_u32(smem_raw) + 127u) & ~127u;
-    uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
-    float* planes = reinterpret_cast<float*>(gen_base);                          // [CT][plane_stride]
-    const uint32_t plane_bytes = (uint32_t)CT * cfg.plane_stride * 4;            // multiple of 128
-    const uint32_t arg_box = (uint32_t)RT * BW * 2;                              // multiple of 128
-    const uint32_t grad_box = (uint32_t)RT * BW * sizeof(GradT);
-    const uint32_t arg_stage = nbox * arg_box, grad_stage = nbox * grad_box;
-    const uint32_t ring_off = plane_bytes;
-    const uint32_t bar_off = ring_off + S * (arg_stage + grad_stage);
-    auto full_bar = [&](int st) { return base + bar_off + 8u * st; };
-    auto empty_bar = [&](int st) { return base + bar_off + 8u * (S + st); };
-    auto turn_bar = [&](int cw) { return base + bar_off + 16u * S + 8u * cw; };   // [NCW]
-    const uint32_t meta_off = bar_off + 16u * S + 8u * (kBwdFastMaxCT / 2 * KW);
-    BwdMeta* s_meta = reinterpret_cast<BwdMeta*>(gen_base + meta_off);           // [S][kBwdFastMaxRT]
-    float* s_dummy = reinterpret_cast<float*>(s_meta + S * kBwdFastMaxRT);        // [32] idle-lane targets
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int groups = (C + CT - 1) / CT;
-    int bid = blockIdx.x;
-    const int band = bid % cfg.bands;
-    bid /= cfg.bands;
-    const int c0 = (bid % groups) * CT;
-    const int b = bid / groups;
-    const int HW = H * W;
-    const int band_lo = min(band * cfg.band_rows, H) * W;
-    const int band_hi = min((band + 1) * cfg.band_rows, H) * W;
-
-    for (int i = threadIdx.x; i < CT * cfg.plane_stride; i += blockDim.x) planes[i] = 0.f;
-    if (threadIdx.x == 0) {
-        for (int st = 0; st < S; ++st) {
-            mbar_init(full_bar(st), 1);
-            mbar_init(empty_bar(st), NCW);
-        }
-        for (int cw = 0; cw < NCW; ++cw) mbar_init(turn_bar(cw), 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    // rows of this image: the plan's order is stable, so its first / last entries are the smallest / largest row
-    const int seg_lo = img_start[b], seg_hi = img_start[b + 1];
-    const int r_lo = seg_hi > seg_lo ? __ldg(order + seg_lo) : 0;
-    const int r_hi = seg_hi > seg_lo ? __ldg(order + seg_hi - 1) + 1 : 0;
-    const int ntiles = (r_hi - r_lo + RT - 1) / RT;
-    const int total_cols = C * PP;
-    const int col0 = c0 * PP;
-    const int col_a = col0 & ~7;                                   // box start: 16-byte aligned column
-    const int col_g = col0 & ~(16 / (int)sizeof(GradT) - 1);
-
-    if (warp == NCW) {
-        // ---- producer warp: lane 0 drives the barriers and TMA, lanes < RT publish each roi's scale and colouring ----
-        uint32_t tx = 0;
-        for (int bx = 0; bx < nbox; ++bx) {
-            if (col_a + bx * BW < total_cols) tx += arg_box;
-            if (col_g + bx * BW < total_cols) tx += grad_box;
-        }
-        int st = 0;
-        uint32_t phase = 0;
-        for (int t = 0; t < ntiles; ++t) {
-            const int r0 = r_lo + t * RT;
-            BwdMeta meta;
-            meta.scale = 0.f;
-            meta.code = 0;
-            if (lane < RT && r0 + lane < r_hi) {
-                const uint2 tail = __ldg(reinterpret_cast<const uint2*>(rec + r0 + lane) + 7);   // bytes 56..63
-                if ((int)(tail.x >> 16) == b) {
-                    meta.scale = __uint_as_float(tail.y);
-                    meta.code = 1 | ((tail.x & 0xFFu) << 8) | (((tail.x >> 8) & 0xFFu) << 16);
-                }
-            }
-            mbar_wait(empty_bar(st), phase ^ 1u);
-            if (lane < RT) s_meta[st * kBwdFastMaxRT + lane] = meta;
-            __syncwarp();
-            if (lane == 0) {
-                mbar_expect_tx(full_bar(st), tx);
-                const uint32_t sa = base + ring_off + st * (arg_stage + grad_stage);
-                const uint32_t sg = sa + arg_stage;
-                for (int bx = 0; bx < nbox; ++bx) {
-                    if (col_a + bx * BW < total_cols) tma_load_2d(sa + bx * arg_box, &tmap_arg, full_bar(st), col_a + bx * BW, r0);
-                    if (col_g + bx * BW < total_cols) tma_load_2d(sg + bx * grad_box, &tmap_grad, full_bar(st), col_g + bx * BW, r0);
-                }
-            }
-            if (++st == S) {
-                st = 0;
-                phase ^= 1u;
-            }
-        }
-    } else if (warp < NCW) {
-        // ---- consumer warps.  KW warps serve one pair of planes; the rois (slots) of the stream are dealt to them
-        // round-robin.  A warp PREPARES its roi -- operands of every colour step fetched from the ring and turned into
-        // (shared address, scaled gradient) pairs in registers -- while its predecessors are still accumulating, then
-        // waits for the turn token, runs the ordered read-add-write steps and passes the token on.
-        const int pair = warp / KW, q = warp - pair * KW;
-        const int half = lane >> 4, la = (lane >> 2) & 3, lb = lane & 3;
-        const int chan = 2 * pair + half;
-        const bool chan_ok = chan < CT && (c0 + chan) < C;
-        uint32_t my_s = smem_u32(planes + (chan_ok ? chan : 0) * cfg.plane_stride);
-        uint32_t dummy_s = smem_u32(s_dummy) + 4u * lane;
-        asm volatile("mov.u32 %0, %0;" : "+r"(my_s));       // keep both in registers
-        asm volatile("mov.u32 %0, %0;" : "+r"(dummy_s));
-        const int ea0 = chan * PP + (col0 - col_a);
-        const int eg0 = chan * PP + (col0 - col_g);
-        const unsigned band_cells = (unsigned)(band_hi - band_lo);
-        const int wrap = (RT - 1) * BW;          // elements skipped when an entry falls into the second box
-        const uint32_t ring_s = base + ring_off;
-        const uint32_t stage_bytes = arg_stage + grad_stage;
-        const uint32_t my_turn = turn_bar(warp), prev_turn = turn_bar(pair * KW + (q + KW - 1) % KW);
-        // strides 2 x 2 (every roi at least 7 x 7 cells): the lane's four bins sit at constant offsets
-        constexpr int kCode22 = 1 | (2 << 8) | (2 << 16);
-        int e22a[4], e22g[4];
-        bool v22[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int ph = 2 * la + (k >> 1), pw = 2 * lb + (k & 1);
-            v22[k] = chan_ok && ph < kPlanP && pw < kPlanP;
-            int e = ea0 + ph * kPlanP + pw;
-            e22a[k] = e + (e >= BW ? wrap : 0);
-            e = eg0 + ph * kPlanP + pw;
-            e22g[k] = e + (e >= BW ? wrap : 0);
-        }
-
-        int st = 0;
-        uint32_t phase = 0;
-        int slot = 0;          // global slot counter of the stream
-        int mine = 0;          // slots this warp has handled so far
-        for (int t = 0; t < ntiles; ++t) {
-            mbar_wait(full_bar(st), phase);
-            const uint32_t sa = ring_s + st * stage_bytes;      // arg-max boxes of this stage
-            const uint32_t sg = sa + arg_stage;                 // grad boxes
-            const BwdMeta* metas = s_meta + st * kBwdFastMaxRT;
-            for (int rr = 0; rr < RT; ++rr, ++slot) {
-                if (slot % KW != q) continue;
-                const BwdMeta m = metas[rr];
-                const int mh = (m.code >> 8) & 0xFF, mw = (m.code >> 16) & 0xFF;
-                const int nsteps = mh * mw;                     // 0 for a roi of another image
-                const int rowe = rr * BW;
-                uint32_t addr[kBwdMaxSteps];
-                float val[kBwdMaxSteps];
-                auto operand = [&](int ea, int eg, uint32_t& ad, float& vl) {
-                    unsigned a, graw;
-                    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(a) : "r"(sa + 2u * (unsigned)(ea + rowe)));
-                    if (sizeof(GradT) == 2) {
-                        asm volatile("ld.shared.u16 %0, [%1];" : "=r"(graw) : "r"(sg + 2u * (unsigned)(eg + rowe)));
-                        graw <<= 16;
-                    } else {
-                        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(graw) : "r"(sg + 4u * (unsigned)(eg + rowe)));
-                    }
-                    const unsigned rel = a - (unsigned)band_lo;   // empty bin (0xFFFF) and other bands fail the test
-                    const bool ok = rel < band_cells;
-                    ad = ok ? my_s + 4u * rel : dummy_s;
-                    vl = ok ? __uint_as_float(graw) * m.scale : 0.f;
-                };
-                bool token = false;
-                auto take_turn = [&]() {
-                    if (!token) {
-                        if (!(q == 0 && mine == 0)) mbar_spin(prev_turn, (uint32_t)((q == 0 ? mine - 1 : mine) & 1));
-                        token = true;
-                    }
-                };
-                if (m.code == kCode22) {
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        addr[k] = dummy_s;
-                        val[k] = 0.f;
-                        if (v22[k]) operand(e22a[k], e22g[k], addr[k], val[k]);
-                    }
-                    take_turn();
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        float v;
-                        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr[k]) : "memory");
-                        v += val[k];
-                        asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr[k]), "f"(v) : "memory");
-                        __syncwarp();   // colour classes of one roi may share cells: order the steps
-                    }
-                } else if (nsteps > 0) {
-                    const int bin0 = la * mh * kPlanP + lb * mw;
-                    const int ih = chan_ok ? min(mh, kPlanP - la * mh) : 0;   // <= 0: block outside the grid
-                    const int jw = min(mw, kPlanP - lb * mw);
-                    int i = 0, j = 0;
-                    for (int s0 = 0; s0 < nsteps; s0 += kBwdMaxSteps) {
-                        const int n = min(kBwdMaxSteps, nsteps - s0);
-#pragma unroll
-                        for (int k = 0; k < kBwdMaxSteps; ++k) {
-                            addr[k] = dummy_s;
-                            val[k] = 0.f;
-                            if (k < n) {
-                                if (i < ih && j < jw) {
-                                    const int bin = bin0 + i * kPlanP + j;
-                                    int ea = ea0 + bin, eg = eg0 + bin;
-                                    ea += (ea >= BW ? wrap : 0);
-                                    eg += (eg >= BW ? wrap : 0);
-                                    operand(ea, eg, addr[k], val[k]);
-                                }
-                                if (++j == mw) {
-                                    j = 0;
-                                    ++i;
-                                }
-                            }
-                        }
-                        take_turn();
-#pragma unroll
-                        for (int k = 0; k < kBwdMaxSteps; ++k) {
-                            if (k < n) {
-                                float v;
-                                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr[k]) : "memory");
-                                v += val[k];
-                                asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr[k]), "f"(v) : "memory");
-                                __syncwarp();
-                            }
-                        }
-                    }
-                } else {
-                    take_turn();
-                }
-                __syncwarp();
-                if (lane == 0) mbar_arrive(my_turn);   // release: the next warp sees this roi's updates
-                ++mine;
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(empty_bar(st));
-            if (++st == S) {
-                st = 0;
-                phase ^= 1u;
-            }
-        }
-    }
-    __syncthreads();
-    const int band_cells = band_hi - band_lo;
-    for (int c = 0; c < CT && c0 + c < C; ++c) {
-        float* dst = grad_feat + ((size_t)b * C + c0 + c) * HW + band_lo;
-        const float* src = planes + c * cfg.plane_stride;
-        for (int i = threadIdx.x; i < band_cells; i += blockDim.x) dst[i] = src[i];
-    }
-}
-
-static bool pick_bwd_fast_cfg(int n, int c, int h, int w, int grad_bytes, BwdFastCfg* out) {
-    const int max_smem = device_max_smem();
-    const int sms = device_num_sms();
-    const int align_elems = 16 / (2 < grad_bytes ? 2 : grad_bytes);
-    bool found = false;
-    double best_cost = 0;
-    for (int bands = 1; bands <= 64; ++bands) {
-        const int band_rows = (h + bands - 1) / bands;
-        if (bands > 1 && (long long)(bands - 1) * band_rows >= h) continue;  // empty last band
-        const int plane_stride = ((band_rows * w + 31) / 32) * 32;
-        for (int CT = kBwdFastMaxCT; CT >= 1; --CT) {
-            if (CT > c) continue;
-            const int cols = CT * kPP + align_elems - 1;   // + the alignment remainder of the first column
-            const int nbox = (cols + 247) / 248;
-            const int BW = (((cols + nbox - 1) / nbox) + 7) / 8 * 8;
-            if (BW > 256 || nbox > 2) continue;
-            const size_t fixed = (size_t)CT * plane_stride * 4 + 128 /*align*/ + 1536 /*barriers, roi meta, dummies*/;
-            for (int RT = kBwdFastMaxRT; RT >= 4; RT >>= 1) {
-                const size_t stage = (size_t)nbox * RT * BW * (2 + grad_bytes);
-                if (fixed + 2 * stage > (size_t)max_smem) continue;
-                int stages = (int)(((size_t)max_smem - fixed) / stage);
-                if (stages > 6) stages = 6;
-                const long long ctas = (long long)n * ((c + CT - 1) / CT) * bands;
-                const long long waves = (ctas + sms - 1) / sms;
-                // every CTA streams all rois of its image once and the chains of its planes advance together:
-                // time ~ waves; an odd CT leaves half a warp idle; prefer deeper rings
-                const double cost = (double)waves + (stages < 3 ? 0.03 : 0.0) + ((CT & 1) ? 0.01 : 0.0);
-                if (!found || cost < best_cost - 1e-9) {
-                    found = true;
-                    best_cost = cost;
-                    out->CT = CT;
-                    out->bands = bands;
-                    out->band_rows = band_rows;
-                    out->nbox = nbox;
-                    out->BW = BW;
-                    out->stages = stages;
-                    out->RT = RT;
-                    out->plane_stride = plane_stride;
-                    out->smem = fixed + (size_t)stages * stage;
-                }
-                if (stages >= 3) break;  // smaller RT only to deepen a shallow ring
-            }
-        }
-        if (found && best_cost < 1.5) break;
-    }
-    return found;
-}
-
-template <typename GradT>
-static int launch_bwd_fast_t(const void* grad, long long ld_grad, const uint16_t* argmax, int R, const void* plan, int n,
-                             int c, int h, int w, float* grad_feat, cudaStream_t st) {
-    BwdFastCfg cfg;
-    if (!pick_bwd_fast_cfg(n, c, h, w, (int)sizeof(GradT), &cfg)) return 0;
-    CUtensorMap ta, tg;
-    int rc = make_tmap_2d(&ta, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, argmax, R, (long long)c * kPP, (long long)c * kPP, cfg.BW,
-                          cfg.RT, CU_TENSOR_MAP_SWIZZLE_NONE);
-    if (rc) return rc;
-    rc = make_tmap_2d(&tg, sizeof(GradT) == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
-                      (int)sizeof(GradT), grad, R, (long long)c * kPP, ld_grad, cfg.BW, cfg.RT, CU_TENSOR_MAP_SWIZZLE_NONE);
-    if (rc) return rc;
-    const PlanView pv = plan_view(plan, R);
-    const int grid = n * ((c + cfg.CT - 1) / cfg.CT) * cfg.bands;
-    const int threads = ((cfg.CT + 1) / 2 * kBwdKW + 1) * 32;
-    auto kern = roi_pool_bwd_fast_kernel<GradT>;
-    SOSWSOD_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem));
-    kern<<<grid, threads, cfg.smem, st>>>(ta, tg, pv.img_start, pv.order, pv.rec, c, h, w, grad_feat, cfg);
-    SOSWSOD_CHECK_LAUNCH();
-    return 1;
-}
-
 // ------------------------------------------------------------------------------------------------
-// backward, queued (v8).  Measured on the turn-token kernel above (ncu, per-instruction samples): the ordered
-// read-add-write chain of a plane pair costs ~200 cycles per roi, everything around it (operand preparation, token
-// hand-off, barrier probes at 90-150 cycles each) another ~400.  Here every plane pair has ONE accumulator warp that
-// does nothing but consume a stream of ready-made steps, fed through a shared-memory queue:
+// backward, queued.  The ordered read-add-write chain of a plane pair is the critical path (~200 cycles per roi);
+// everything around it (operand fetch, address arithmetic) is taken off that path: every plane pair has ONE
+// accumulator warp that does nothing but consume a stream of ready-made steps, fed through a shared-memory queue.
+// (Measured alternatives, see profiles/README.md: warps handing a turn token around, 628 us; merging a roi's
+// duplicate cells in the prep warps so that its steps become independent, 575 us -- the extra shuffles make the prep
+// warps the bottleneck; this kernel, 440-525 us.)
 //
 //   TMA warp      streams [RT rois x BW columns] tiles of arg-max / grad_out through the mbarrier ring and, per roi,
 //                 publishes (scale, colour strides, first chunk number): the rois' colour steps are cut into CHUNKS
@@ -776,7 +450,7 @@ static int launch_bwd_fast_t(const void* grad, long long ld_grad, const uint16_t
 // steps of a chunk in order 0..3; the accumulator reads them in order 3..0 and checks step 3's tag in every lane:
 // shared-memory requests of an SM are served in order, so a current step 3 implies current steps 0..2.  Slots return
 // to the prep warps through one counter per plane pair (chunks consumed so far; single writer).
-// Result: deterministic (fixed order per plane), atomic-free, bit-identical to the turn-token kernel.
+// Result: deterministic (fixed order per plane), atomic-free.
 constexpr int kBwdQSteps = 4;                       // colour steps per chunk / queue slot
 constexpr int kBwdQSlotBytes = kBwdQSteps * 32 * 8;
 constexpr int kBwdQMaxP = 6;
@@ -1112,9 +786,13 @@ roi_pool_bwd_q_kernel(const __grid_constant__ CUtensorMap tmap_arg, const __grid
     }
 }
 
-static int env_int(const char* name, int dflt) {
-    const char* e = getenv(name);
-    return e ? atoi(e) : dflt;
+// Tuning overrides, read ONCE per process (0 = let the search decide).
+static int env_int_once(const char* name, int* cache) {
+    if (*cache < 0) {
+        const char* e = getenv(name);
+        *cache = e ? atoi(e) : 0;
+    }
+    return *cache;
 }
 
 static bool pick_bwd_q_cfg(int n, int c, int h, int w, int grad_bytes, BwdQCfg* out) {
@@ -1122,7 +800,8 @@ static bool pick_bwd_q_cfg(int n, int c, int h, int w, int grad_bytes, BwdQCfg* 
     const int sms = device_num_sms();
     const int align_elems = 16 / (2 < grad_bytes ? 2 : grad_bytes);
     // tuning overrides (0 = let the search decide)
-    const int force_p = env_int("SOSWSOD_BWDQ_P", 0), force_lq = env_int("SOSWSOD_BWDQ_LQ", 0);
+    static int env_p = -1, env_lq = -1;
+    const int force_p = env_int_once("SOSWSOD_BWDQ_P", &env_p), force_lq = env_int_once("SOSWSOD_BWDQ_LQ", &env_lq);
     bool found = false;
     double best_cost = 0;
     for (int bands = 1; bands <= 64; ++bands) {
@@ -1180,8 +859,25 @@ static bool pick_bwd_q_cfg(int n, int c, int h, int w, int grad_bytes, BwdQCfg* 
 template <typename GradT>
 static int launch_bwd_q_t(const void* grad, long long ld_grad, const uint16_t* argmax, int R, const void* plan, int n, int c,
                           int h, int w, float* grad_feat, cudaStream_t st) {
-    BwdQCfg qc;
-    if (!pick_bwd_q_cfg(n, c, h, w, (int)sizeof(GradT), &qc)) return 0;
+    // the configuration search depends on the shape only: remembered per host thread for the shapes of a step
+    struct Memo {
+        int n, c, h, w, found;
+        BwdQCfg qc;
+    };
+    static thread_local Memo memo[4] = {};
+    static thread_local int memo_next = 0;
+    const Memo* hit = nullptr;
+    for (const Memo& m : memo)
+        if (m.found != 0 && m.n == n && m.c == c && m.h == h && m.w == w) hit = &m;
+    if (!hit) {
+        Memo& m = memo[memo_next];
+        memo_next = (memo_next + 1) & 3;
+        m.n = n; m.c = c; m.h = h; m.w = w;
+        m.found = pick_bwd_q_cfg(n, c, h, w, (int)sizeof(GradT), &m.qc) ? 1 : -1;
+        hit = &m;
+    }
+    if (hit->found < 0) return 0;
+    const BwdQCfg qc = hit->qc;
     const BwdFastCfg& cfg = qc.b;
     CUtensorMap ta, tg;
     int rc = make_tmap_2d(&ta, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, argmax, R, (long long)c * kPP, (long long)c * kPP, cfg.BW,
@@ -1194,22 +890,13 @@ static int launch_bwd_q_t(const void* grad, long long ld_grad, const uint16_t* a
     const int grid = n * ((c + cfg.CT - 1) / cfg.CT) * cfg.bands;
     const int threads = ((cfg.CT + 1) / 2 * (1 + qc.P) + 1) * 32;
     auto kern = roi_pool_bwd_q_kernel<GradT>;
-    SOSWSOD_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem));
+    SOSWSOD_ENSURE_SMEM(kern, cfg.smem);
     kern<<<grid, threads, cfg.smem, st>>>(ta, tg, pv.img_start, pv.order, pv.rec, c, h, w, grad_feat, qc);
     SOSWSOD_CHECK_LAUNCH();
     return 1;
 }
 
-// SOSWSOD_ROI_BWD=turn selects the turn-token kernel (v7) instead of the queued one (v8); read once.
-static bool bwd_use_queue() {
-    static int v = -1;
-    if (v < 0) {
-        const char* e = getenv("SOSWSOD_ROI_BWD");
-        v = (e && e[0] == 't') ? 0 : 1;
-    }
-    return v == 1;
-}
-
+// Returns 1 when the queued kernel ran, 0 when no configuration fits (the caller takes the general kernel), < 0 on error.
 int launch_bwd_fast(const void* grad, int grad_dtype, long long ld_grad, const uint16_t* argmax, int R, const void* plan,
                     int n, int c, int h, int w, float* grad_feat, cudaStream_t st) {
     if (n > kPlanMaxImages) return 0;
@@ -1217,15 +904,9 @@ int launch_bwd_fast(const void* grad, int grad_dtype, long long ld_grad, const u
     const bool aligned = ((uintptr_t)grad & 15) == 0 && ((uintptr_t)argmax & 15) == 0 && ((ld_grad * gb) & 15) == 0 &&
                          (((long long)c * kPP * 2) & 15) == 0;
     if (!aligned) return 0;
-    if (bwd_use_queue()) {
-        const int rc = grad_dtype == SOSWSOD_DTYPE_BF16
-                           ? launch_bwd_q_t<__nv_bfloat16>(grad, ld_grad, argmax, R, plan, n, c, h, w, grad_feat, st)
-                           : launch_bwd_q_t<float>(grad, ld_grad, argmax, R, plan, n, c, h, w, grad_feat, st);
-        if (rc != 0) return rc;   // 0: no queued configuration fits; fall through to the turn-token kernel
-    }
-    if (grad_dtype == SOSWSOD_DTYPE_BF16)
-        return launch_bwd_fast_t<__nv_bfloat16>(grad, ld_grad, argmax, R, plan, n, c, h, w, grad_feat, st);
-    return launch_bwd_fast_t<float>(grad, ld_grad, argmax, R, plan, n, c, h, w, grad_feat, st);
+    return grad_dtype == SOSWSOD_DTYPE_BF16
+               ? launch_bwd_q_t<__nv_bfloat16>(grad, ld_grad, argmax, R, plan, n, c, h, w, grad_feat, st)
+               : launch_bwd_q_t<float>(grad, ld_grad, argmax, R, plan, n, c, h, w, grad_feat, st);
 }
 
 }  // namespace soswsod

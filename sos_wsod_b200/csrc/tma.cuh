@@ -73,8 +73,39 @@ inline PFN_encodeTiled get_encode_fn() {
 
 // 2-D tensor map over a row-major [rows, cols] matrix with leading dimension ld (elements of elem_bytes);
 // box = {box_cols (inner), box_rows}.  Out-of-bounds box elements are zero-filled.
+// Encoded maps are cached per host thread (direct-mapped, 128 entries keyed on every argument): a training step re-uses
+// the same few dozen (pointer, shape, box) combinations step after step -- the caching allocator hands the same
+// blocks back -- so the driver call (~1-2 us each, two per GEMM / ROI-backward launch) is paid once.
+struct TmapKey {
+    const void* base;
+    long long rows, cols, ld;
+    int dtype, elem_bytes, box_cols, box_rows, swizzle;
+    bool operator==(const TmapKey& o) const {
+        return base == o.base && rows == o.rows && cols == o.cols && ld == o.ld && dtype == o.dtype &&
+               elem_bytes == o.elem_bytes && box_cols == o.box_cols && box_rows == o.box_rows && swizzle == o.swizzle;
+    }
+};
+struct TmapSlot {
+    TmapKey key;
+    CUtensorMap map;
+    bool valid;
+};
+inline TmapSlot* tmap_cache() {
+    static thread_local TmapSlot slots[128] = {};
+    return slots;
+}
+
 inline int make_tmap_2d(CUtensorMap* map, CUtensorMapDataType dtype, int elem_bytes, const void* base, long long rows,
                         long long cols, long long ld, int box_cols, int box_rows, CUtensorMapSwizzle swizzle) {
+    const TmapKey key{base, rows, cols, ld, (int)dtype, elem_bytes, box_cols, box_rows, (int)swizzle};
+    unsigned long long hsh = reinterpret_cast<unsigned long long>(base) * 0x9E3779B97F4A7C15ull;
+    hsh ^= (unsigned long long)rows * 0xBF58476D1CE4E5B9ull + (unsigned long long)cols * 0x94D049BB133111EBull +
+           (unsigned long long)ld * 31ull + (unsigned long long)(box_cols * 131 + box_rows * 17 + (int)dtype * 7 + (int)swizzle);
+    TmapSlot& slot = tmap_cache()[(hsh >> 32) & 127u];
+    if (slot.valid && slot.key == key) {
+        *map = slot.map;
+        return SOSWSOD_OK;
+    }
     PFN_encodeTiled enc = get_encode_fn();
     if (!enc) {
         set_error("cuTensorMapEncodeTiled not available from the driver");
@@ -91,6 +122,9 @@ inline int make_tmap_2d(CUtensorMap* map, CUtensorMapDataType dtype, int elem_by
                   ld, box_cols, box_rows);
         return SOSWSOD_ERR_CUDA;
     }
+    slot.key = key;
+    slot.map = *map;
+    slot.valid = true;
     return SOSWSOD_OK;
 }
 

@@ -119,14 +119,27 @@ def roi_pool_backward(grad_out: torch.Tensor, argmax: torch.Tensor, rois: torch.
     if grad_out.stride(-1) != 1:
         grad_out = grad_out.contiguous()
     rois = rois.contiguous()
-    grad_feat = torch.empty((n, c, h, w), dtype=torch.float32, device=grad_out.device)
     if m == 0:
-        return grad_feat.zero_()
+        return torch.zeros((n, c, h, w), dtype=torch.float32, device=grad_out.device)
+    argmax = argmax.contiguous()
+    # The kernels stream grad / arg-max rows with TMA: 16-byte aligned rows.  Odd channel counts are padded with empty
+    # channels (arg-max -1, zero gradient) instead of falling back to atomics -- there is no atomic path.
+    row_a = c * ph * pw * argmax.element_size()
+    row_g = grad_out.stride(0) * grad_out.element_size()
+    if row_a % 16 or row_g % 16 or grad_out.data_ptr() % 16:
+        cp = (c + 7) // 8 * 8
+        g2 = torch.zeros((m, cp * ph * pw), dtype=grad_out.dtype, device=grad_out.device)
+        g2[:, :c * ph * pw] = grad_out[:, :c * ph * pw]
+        a2 = torch.full((m, cp, ph, pw), -1, dtype=argmax.dtype, device=argmax.device)
+        a2[:, :c] = argmax.view(m, c, ph, pw)
+        out = roi_pool_backward(g2, a2, rois, (n, cp, h, w), pooled, row_scale, row_scale_bias, spatial_scale, plan)
+        return out[:, :c].contiguous()
+    grad_feat = torch.empty((n, c, h, w), dtype=torch.float32, device=grad_out.device)
     a_dt = ARGMAX_U16 if argmax.dtype == torch.int16 else ARGMAX_I32
     if row_scale is not None:
         row_scale = row_scale.contiguous().float()
     lib = _lib.load()
-    check(lib.soswsod_roi_pool_backward(_ptr(grad_out), _dt(grad_out), grad_out.stride(0), _ptr(argmax.contiguous()), a_dt,
+    check(lib.soswsod_roi_pool_backward(_ptr(grad_out), _dt(grad_out), grad_out.stride(0), _ptr(argmax), a_dt,
                                         _ptr(rois), m, _ptr(row_scale), float(row_scale_bias), n, c, h, w, ph, pw,
                                         float(spatial_scale), _ptr(grad_feat), _ptr(plan),
                                         0 if plan is None else plan.numel(), _stream()), "roi_pool_backward")
