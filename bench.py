@@ -523,6 +523,9 @@ def run_b200_arm(args):
         ex.begin_step()
         got = eng.train_step(vb, im["gt"], dropout_seeds=(7, 8), grad_hook=heads.grad_hook)
         ex.wait_gradients()
+        bytes_step = dict(ex.bytes_last_step)
+        if ex.mode == "sharded":      # the operand all-gather the optimizer would start: bf16 rows of the same panels
+            bytes_step["all_gather"] = bytes_step["reduce_scatter"] // 2
         errs = []
         for key, want in (("fc1_w", want6), ("fc2_w", want7)):
             for lo, hi in ex.owned_rows(key):
@@ -533,7 +536,7 @@ def run_b200_arm(args):
         ex.begin_step()       # drop this step's pending state: no optimizer consumes it
         exchange_check = {"mode": ex.mode, "max_rel_err_vs_nccl_allreduce_avg": err, "ok": bool(err < 1e-5),
                           "rows_checked": "the rows each rank owns after the exchange (fc1.weight, fc2.weight)",
-                          "differs_from_local_gradient": bool(other > 0), "bytes_per_step": dict(ex.bytes_last_step)}
+                          "differs_from_local_gradient": bool(other > 0), "bytes_per_rank_per_step": bytes_step}
         del local, got, want6, want7
 
     # ---- end to end through the plugin surface, host buffers, H2D/D2H inside the timed region ----
