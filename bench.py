@@ -263,7 +263,19 @@ def init_dist(dev):
     # NCCL's INFO lines (the driver counts ranks from them) must not land on stdout, which carries ONE json line
     if os.environ.get("NCCL_DEBUG") and not os.environ.get("NCCL_DEBUG_FILE"):
         os.environ["NCCL_DEBUG_FILE"] = "/dev/stderr"
-    dist.init_process_group("nccl", device_id=dev)
+    # ... and its version banner is printed with a bare printf: point fd 1 at stderr while the communicator comes up
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        dist.init_process_group("nccl", device_id=dev)
+        t = torch.zeros(1, device=dev)
+        dist.all_reduce(t)
+        torch.cuda.synchronize()
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved, 1)
+        os.close(saved)
     return dist
 
 
@@ -381,7 +393,8 @@ def run_b200_arm(args):
 
     # ---- device-resident throughput ----
     sampler = ClockSampler(local_rank)
-    sampler.start()
+    if rank == 0:          # one poller per job: eight nvidia-smi loops contend for the driver with the ranks' launches
+        sampler.start()
     for i in range(PRE_WARMUP + args.warmup):
         device_step(i)
     settle_blocks = settle(lambda j: device_step(j))
@@ -808,13 +821,17 @@ def run_detect_arm(args):
     writer = PascalVOCDetectionWriter("voc_2007_synthetic", [f"c{k}" for k in range(C)],
                                       os.path.join(args.out_dir, "detection_results_{}.json"))
     os.makedirs(args.out_dir, exist_ok=True)
-    res = {"boxes": torch.zeros((BLOCK, topk, 4), device=dev), "scores": torch.zeros((BLOCK, topk), device=dev),
-           "classes": torch.zeros((BLOCK, topk), dtype=torch.int32, device=dev), "counts": torch.zeros((BLOCK,), dtype=torch.int32, device=dev)}
-    host_res = {k: torch.empty(v.shape, dtype=v.dtype, pin_memory=True) for k, v in res.items()}
-    h2d_bytes = R * 4 * 4 + R * 4
-    d2h_bytes = sum(v[0].numel() * v.element_size() for v in res.values())
+    # results of BLOCK images per device->host copy, double-buffered: the host formats block k while the device runs k + 1
+    def result_set():
+        r = {"boxes": torch.zeros((BLOCK, topk, 4), device=dev), "scores": torch.zeros((BLOCK, topk), device=dev),
+             "classes": torch.zeros((BLOCK, topk), dtype=torch.int32, device=dev), "counts": torch.zeros((BLOCK,), dtype=torch.int32, device=dev)}
+        return r, {k: torch.empty(v.shape, dtype=v.dtype, pin_memory=True) for k, v in r.items()}
 
-    def one_image(idx, slot):
+    sets = [result_set(), result_set()]
+    h2d_bytes = R * 4 * 4 + R * 4
+    d2h_bytes = sum(v[0].numel() * v.element_size() for v in sets[0][0].values())
+
+    def one_image(idx, res, slot):
         feats, boxes_h, obj_h = pool[idx % len(pool)]
         boxes = boxes_h.to(dev, non_blocking=True)
         obj = obj_h.to(dev, non_blocking=True)
@@ -831,21 +848,32 @@ def run_detect_arm(args):
         res["counts"][slot:slot + 1].copy_(nd)
         return dropped
 
-    def flush(ids):
+    pending = []
+
+    def start_flush(ids, which):
+        res, host_res = sets[which]
         n = len(ids)
         for k in res:
             host_res[k][:n].copy_(res[k][:n], non_blocking=True)
-        torch.cuda.synchronize()
+        ev = torch.cuda.Event()
+        ev.record()
+        pending.append((ids, host_res, ev))
+
+    def finish_flush():
+        ids, host_res, ev = pending.pop(0)
+        ev.synchronize()
+        n = len(ids)
         writer.process_arrays(ids, host_res["boxes"][:n].numpy(), host_res["scores"][:n].numpy(),
                               host_res["classes"][:n].numpy(), host_res["counts"][:n].numpy())
 
     for i in range(max(3, args.warmup)):
-        one_image(i, 0)
+        one_image(i, sets[0][0], 0)
     torch.cuda.synchronize()
     writer.reset()
     sampler = ClockSampler(local_rank)
-    sampler.start()
-    sampler.wait_first_sample()
+    if rank == 0:
+        sampler.start()
+        sampler.wait_first_sample()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
@@ -853,17 +881,22 @@ def run_detect_arm(args):
     w0 = time.perf_counter()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    ids = []
+    ids, which = [], 0
     for idx in mine:
-        one_image(idx, len(ids))
+        one_image(idx, sets[which][0], len(ids))
         ids.append(idx)
         if len(ids) == BLOCK:
-            flush(ids)
-            ids = []
+            start_flush(ids, which)
+            ids, which = [], which ^ 1
+            if len(pending) == 2:      # the set about to be reused must have been formatted
+                finish_flush()
     if ids:
-        flush(ids)
+        start_flush(ids, which)
     e1.record()
+    while pending:
+        finish_flush()
     torch.cuda.synchronize()
+    t_gen = time.perf_counter() - w0
     dev_ms = e0.elapsed_time(e1)
     path = writer.save()          # the one gather of the rows to rank 0 + the json dump (host)
     if world > 1:
@@ -872,10 +905,10 @@ def run_detect_arm(args):
     sampler.window(w0, time.perf_counter())
     clocks = sampler.stop()
     launches = ops.COUNTERS["launches"] - n0
-    tm = torch.tensor([dev_ms, wall_s * 1e3], dtype=torch.float64, device=dev)
+    tm = torch.tensor([dev_ms, wall_s * 1e3, t_gen * 1e3], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-    dev_ms, wall_ms = float(tm[0]), float(tm[1])
+    dev_ms, wall_ms, gen_ms = float(tm[0]), float(tm[1]), float(tm[2])
     if rank == 0:
         rows = json.load(open(path))
         value = args.images / (wall_ms / 1e3)
@@ -884,6 +917,8 @@ def run_detect_arm(args):
                 "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
                 "image_views_per_s": value * V, "proposals_per_s": value * V * R,
                 "device_ms_per_image_rank_max": dev_ms / len(mine), "images_per_rank": len(mine),
+                "generation_s_rank_max": gen_ms / 1e3, "gather_and_json_dump_s": (wall_ms - gen_ms) / 1e3,
+                "generation_images_per_s": args.images / (gen_ms / 1e3),
                 "config": {"workload": f"cfg5: test-time detection-result generation, {args.images} synthetic 480x640 images sharded "
                                        f"by InferenceSampler blocks over {world} GPU(s), {V} views ({len(scales)} scales x h-flip) x {R} "
                                        f"proposals, C={C}, K={REFINE_K}: proposal transform -> ROI pool + fc6/fc7 + heads (all views, one "

@@ -103,6 +103,14 @@ def test_product_writers_are_byte_compatible(gold, tmp_path):
     voc2 = PascalVOCDetectionWriter("voc_2007_test", [f"c{k}" for k in range(gold["num_classes"])], str(tmp_path / "blk_{}.json"))
     voc2.process_arrays([d["image_id"] for d in per], boxes, scores, classes, counts)
     assert open(voc2.save()).read() == gold["voc_json"]
+    # the directly assembled text is what json.dumps renders (incl. float reprs like 1e-05, inf-free by construction)
+    import json as _json
+
+    voc3 = PascalVOCDetectionWriter("x", ["a", "b"], str(tmp_path / "t_{}.json"))
+    voc3._predictions[0] += ["7 0.000 1.0 2.5 1e-05 123456789.1", "8 1.000 0.1 0.2 0.3 0.4"]
+    voc3._predictions[1] += ["9 0.500 10.0 20.0 30.0 40.0"]
+    assert voc3.json_text() == _json.dumps(voc3.rows())
+    assert PascalVOCDetectionWriter("x", ["a"], "y").json_text() == "[]"
 
 
 _SHARD_SCRIPT = r'''
