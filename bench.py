@@ -821,9 +821,12 @@ def run_detect_arm(args):
     topk = cfg.TEST.DETECTIONS_PER_IMAGE
     BLOCK = 64     # images per device->host copy of the results
     mine = inference_shard(args.images, rank, world)
+    import tempfile
+
+    out_dir = args.out_dir or tempfile.mkdtemp(prefix="soswsod_detect_")
+    os.makedirs(out_dir, exist_ok=True)
     writer = PascalVOCDetectionWriter("voc_2007_synthetic", [f"c{k}" for k in range(C)],
-                                      os.path.join(args.out_dir, "detection_results_{}.json"))
-    os.makedirs(args.out_dir, exist_ok=True)
+                                      os.path.join(out_dir, "detection_results_{}.json"))
     # results of BLOCK images per device->host copy, double-buffered: the host formats block k while the device runs k + 1
     def result_set():
         r = {"boxes": torch.zeros((BLOCK, topk, 4), device=dev), "scores": torch.zeros((BLOCK, topk), device=dev),
@@ -914,6 +917,9 @@ def run_detect_arm(args):
     dev_ms, wall_ms, gen_ms = float(tm[0]), float(tm[1]), float(tm[2])
     if rank == 0:
         rows = json.load(open(path))
+        json_bytes = os.path.getsize(path)
+        if args.out_dir is None:
+            os.remove(path)
         value = args.images / (wall_ms / 1e3)
         line = {"metric": "detection-result generation (TTA) images/s", "value": value, "unit": "images/s", "n_gpus": world,
                 "steps": args.images, "warmup": max(3, args.warmup), "ms_per_step": wall_ms / len(mine), "higher_is_better": True,
@@ -932,7 +938,7 @@ def run_detect_arm(args):
                                     "copied host->device per image", "collectives_on_compute_path": 0},
                 "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes},
                 "gpu_launches": int(launches), "gpu_launches_per_image": launches / len(mine), "clocks": clocks,
-                "detection_rows_written": len(rows), "json_path": path, "json_bytes": os.path.getsize(path)}
+                "detection_rows_written": len(rows), "json_path": path if args.out_dir else "(scratch, removed)", "json_bytes": json_bytes}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -954,7 +960,8 @@ def main():
                     help="voc = BASELINE configs[1] (the bench line); coco = configs[3] (80 classes)")
     ap.add_argument("--images", type=int, default=5000, help="detect workload: images in the synthetic dataset")
     ap.add_argument("--scales", type=int, nargs="+", default=[480, 576, 672, 768, 864], help="detect workload: TEST.AUG.MIN_SIZES")
-    ap.add_argument("--out-dir", default=os.path.join(ROOT, "gpurun_out", "detect"))
+    ap.add_argument("--out-dir", default=None, help="detect workload: where the detection_results json goes (default: a "
+                    "scratch directory, removed after the run -- the file is ~45 MB at 5000 images)")
     args = ap.parse_args()
     if args.shape == "coco":
         global NUM_CLASSES, WORKLOAD, CFG_ID
