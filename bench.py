@@ -514,7 +514,16 @@ def run_b200_arm(args):
                      "avg_us_per_launch": 1e3 * tot / max(len(roi_events[kind]), 1), "compulsory_hbm_gbs": gbs,
                      "frac_of_hbm_peak": gbs / peaks["hbm_gbs"]}
     roi["share_of_step"] = (roi["fwd"]["ms_per_step"] + roi["bwd"]["ms_per_step"]) / ev_pass_ms_per_step
-    roi["bound"] = "shared-memory gather / read-add-write inside the SM (planes staged in smem); HBM carries only the compulsory bytes"
+    roi["bound"] = ("shared-memory bandwidth + issue inside the SM: the gather (forward) and the read-add-write (backward) run on "
+                    "planes staged in shared memory; HBM carries only the compulsory bytes, L2 almost nothing")
+    if os.path.exists(tpath):      # the shared-memory pipe utilisation of the same kernels, from the committed ncu capture
+        for kind, key in (("fwd", "roi_pool_fwd"), ("bwd", "roi_pool_bwd")):
+            rows = tj.get(key) or []
+            vals = [r.get("smem_wavefront_pct_of_peak") for r in rows if r.get("smem_wavefront_pct_of_peak") is not None]
+            if vals:
+                roi[kind]["smem_pipe_frac_of_peak_ncu"] = [v / 100.0 for v in vals]
+                roi[kind]["issue_active_frac_ncu"] = [r.get("issue_active_pct", 0.0) / 100.0 for r in rows]
+                roi[kind]["l2_frac_of_peak_ncu"] = [r.get("l2_sectors_pct_of_peak", 0.0) / 100.0 for r in rows]
     roofline["roi_pool"] = roi
     n_params = sum(p.numel() for p in master.values())
     sgd_ms = sum(e0.elapsed_time(e1) for e0, e1 in sgd_events) / ev_steps
@@ -958,15 +967,23 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--shape", default="voc", choices=["voc", "coco"],
                     help="voc = BASELINE configs[1] (the bench line); coco = configs[3] (80 classes)")
+    ap.add_argument("--refine-k", type=int, default=None, help="refinement branches (3 = north_star / the bench line; 4 = the shipped yamls)")
+    ap.add_argument("--proposals", type=int, default=None, help="proposals per view (2000 = the bench line; 4000 = PRECOMPUTED_PROPOSAL_TOPK_TRAIN)")
     ap.add_argument("--images", type=int, default=5000, help="detect workload: images in the synthetic dataset")
     ap.add_argument("--scales", type=int, nargs="+", default=[480, 576, 672, 768, 864], help="detect workload: TEST.AUG.MIN_SIZES")
     ap.add_argument("--out-dir", default=None, help="detect workload: where the detection_results json goes (default: a "
                     "scratch directory, removed after the run -- the file is ~45 MB at 5000 images)")
     args = ap.parse_args()
+    global NUM_CLASSES, WORKLOAD, CFG_ID, REFINE_K, R_PROPOSALS
     if args.shape == "coco":
-        global NUM_CLASSES, WORKLOAD, CFG_ID
         NUM_CLASSES, CFG_ID = 80, 4
         WORKLOAD = WORKLOAD.replace("cfg2:", "cfg4:").replace("VOC07 shape", "COCO shape").replace("C=20", "C=80")
+    if args.refine_k is not None and args.refine_k != REFINE_K:
+        WORKLOAD = WORKLOAD.replace(f"K={REFINE_K}", f"K={args.refine_k}").replace("cfg2:", "cfg2 variant:").replace("cfg4:", "cfg4 variant:")
+        REFINE_K = args.refine_k
+    if args.proposals is not None and args.proposals != R_PROPOSALS:
+        WORKLOAD = WORKLOAD.replace(f"x {R_PROPOSALS} proposals", f"x {args.proposals} proposals").replace("cfg2:", "cfg2 variant:").replace("cfg4:", "cfg4 variant:")
+        R_PROPOSALS = args.proposals
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3
     if args.impl == "reference":

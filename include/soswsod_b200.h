@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define SOSWSOD_ABI_VERSION 7
+#define SOSWSOD_ABI_VERSION 8
 
 #define SOSWSOD_OK 0
 #define SOSWSOD_ERR_INVALID (-1)     /* bad shape / null pointer / misalignment */
@@ -116,11 +116,14 @@ int soswsod_gemm_bf16(const void* a, long long lda, int a_mn_major, const void* 
 int soswsod_dropout_mask(unsigned char* mask, int m, int n, float dropout_p, unsigned long long seed,
                          soswsod_stream_t stream);
 
-/* out[r, c] = bf16(in[r, c] * col_scale[c]) and (optionally) out_t[c, r] = same, in fp32 [rows, ld_in].
- * col_scale may be NULL; out or out_t may be NULL. */
+/* out[r, c] = bf16(in[r, c] * col_scale[c] * m[r, c]) and (optionally) out_t[c, r] = same, in fp32 [rows, ld_in].
+ * m = 1 without mask_src; with it (bf16 [rows, ld_mask], the saved post-ReLU(+dropout) activation)
+ * m = mask_scale where mask_src > 0 and 0 elsewhere -- the backward of F.relu_ + F.dropout of
+ * W/modeling/roi_heads/box_head.py:88-90 applied to an incoming gradient.  col_scale / mask_src may be NULL;
+ * out or out_t may be NULL. */
 int soswsod_cast_f32_bf16(const float* in, long long ld_in, int rows, int cols, const float* col_scale,
                           void* out, long long ld_out, void* out_t, long long ld_out_t,
-                          soswsod_stream_t stream);
+                          const void* mask_src, long long ld_mask, float mask_scale, soswsod_stream_t stream);
 /* out_t[c, r] = in[r, c] for bf16 [rows, ld_in]. */
 int soswsod_transpose_bf16(const void* in, long long ld_in, int rows, int cols, void* out_t,
                            long long ld_out_t, soswsod_stream_t stream);

@@ -37,9 +37,10 @@ for d in rows[2:]:
     e["_us"] = val('gpu__time_duration.sum')
     e["_dram_bytes"] = val('dram__bytes_read.sum') + val('dram__bytes_write.sum')
     launches.append(e)
-# the capture covers launches 18..33 of the process; keep the LAST whole step = from the last ROI forward pair onwards
-summary = {"source": f"ncu --set full --clock-control none --import-source on, bench.py --steps 1 --warmup 3 ({os.path.basename(rep)}); "
-                     "kernels gemm_bf16 / roi_pool_fwd / roi_pool_bwd of the capture window", "launches": launches}
+# the capture window (-s 42 -c 14 over the kernels below) is exactly one step after three warm-up steps: 2 ROI forwards,
+# 9 GEMMs, 2 ROI backwards, the fused SGD launch
+summary = {"source": f"ncu --set full --clock-control none --import-source on -k regex:gemm_bf16|roi_pool_fwd_fast|roi_pool_bwd_q|sgd_multi "
+                     f"-s 42 -c 14, bench.py --steps 2 --warmup 3 --blocks 1 ({os.path.basename(rep)})", "launches": launches}
 json.dump(summary, open(os.path.join(ROOT, "profiles", f"{tag}_ncu_full_summary.json"), "w"), indent=1)
 gem = [l for l in launches if "gemm_bf16_kernel" in l["kernel"]]
 # one step has 9 GEMM launches (fc6, fc7, head forward; head / fc7 / fc6 wgrad + dgrad).  The capture window starts
@@ -51,9 +52,15 @@ traffic = {"source": f"profiles/{tag}_ncu_full_summary.json (ncu --set full, one
                                 "dram_bytes_per_launch_avg": sum(g["_dram_bytes"] for g in gem) / max(len(gem), 1),
                                 "fc6_fwd_dram_bytes": max(gem, key=lambda g: g["_us"])["_dram_bytes"] if gem else None,
                                 "per_launch": [{"kernel": g["kernel"], "dram_bytes": g["_dram_bytes"], "us": g["_us"]} for g in gem]}}
-for kind in ("roi_pool_fwd", "roi_pool_bwd"):
+for kind in ("roi_pool_fwd", "roi_pool_bwd", "sgd_multi"):
     ls = [l for l in launches if kind in l["kernel"]][-2:]
-    traffic[kind] = [{"kernel": l["kernel"], "dram_bytes": l["_dram_bytes"], "us": l["_us"]} for l in ls]
+    def pct(l, key):
+        v = next((val for kk, val in l.items() if kk.startswith(key)), None)
+        return None if v is None else float(v.replace(",", ""))
+    traffic[kind] = [{"kernel": l["kernel"], "dram_bytes": l["_dram_bytes"], "us": l["_us"],
+                      "smem_wavefront_pct_of_peak": pct(l, "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak"),
+                      "issue_active_pct": pct(l, "smsp__issue_active"), "l2_sectors_pct_of_peak": pct(l, "lts__t_sectors.avg.pct"),
+                      "dram_pct_of_peak": pct(l, "gpu__dram_throughput")} for l in ls]
 json.dump(traffic, open(os.path.join(ROOT, "profiles", "ncu_traffic.json"), "w"), indent=1)
 for l in launches:
     print(f"{l['_us']:9.1f} us  dram {l['_dram_bytes']/1e6:9.1f} MB  {l['kernel'][:80]}")

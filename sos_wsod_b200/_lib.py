@@ -10,7 +10,7 @@ from ctypes import c_char_p, c_double, c_float, c_int, c_longlong, c_size_t, c_u
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libsoswsod_b200.so")
-ABI_VERSION = 7
+ABI_VERSION = 8
 
 DTYPE_F32, DTYPE_BF16 = 0, 1
 ARGMAX_I32, ARGMAX_U16 = 0, 1
@@ -31,7 +31,7 @@ SIGNATURES = {
     "soswsod_gemm_bf16": (c_int, [_P, _LL, c_int, _P, _LL, c_int, _P, _LL, c_int, c_int, c_int, c_int, _P, c_int, _P,
                                    _LL, c_float, c_float, c_ulonglong, _P, _P]),
     "soswsod_dropout_mask": (c_int, [_P, c_int, c_int, c_float, c_ulonglong, _P]),
-    "soswsod_cast_f32_bf16": (c_int, [_P, _LL, c_int, c_int, _P, _P, _LL, _P, _LL, _P]),
+    "soswsod_cast_f32_bf16": (c_int, [_P, _LL, c_int, c_int, _P, _P, _LL, _P, _LL, _P, _LL, c_float, _P]),
     "soswsod_transpose_bf16": (c_int, [_P, _LL, c_int, c_int, _P, _LL, _P]),
     "soswsod_colsum_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "soswsod_colsum": (c_int, [_P, c_int, _LL, c_int, c_int, _P, _P, c_size_t, _P]),

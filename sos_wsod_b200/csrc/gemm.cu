@@ -17,6 +17,9 @@
 // Operand layouts in shared memory are the canonical UMMA layouts: K-major SWIZZLE_128B (rows of 64 bf16 =
 // 128 B, 8-row swizzle atoms, SBO = 1024 B) or MN-major SWIZZLE_128B (64 MN elements contiguous per k row,
 // 8-k-row atoms, SBO = 1024 B, LBO = BLOCK_K*128 B between 64-wide MN chunks).
+#include <math.h>
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "tma.cuh"
 
@@ -107,7 +110,7 @@ template <int BLOCK_N, bool A_MN, bool B_MN, bool OUT_BF16>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  void* __restrict__ dptr, long long ldd, int M, int N, int K, GemmEpilogue ep,
-                 unsigned int* __restrict__ sched) {
+                 unsigned int* __restrict__ sched, int group_m) {
     constexpr int kStages = gemm_stages(BLOCK_N);
     constexpr int kABytes = kBlockM * kBlockK * 2;
     constexpr int kBBytes = BLOCK_N * kBlockK * 2;
@@ -169,9 +172,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_ptr_generic;
 
-    // Tile order: groups of 8 m-blocks, n fastest inside a group, so the CTAs resident at one time share a
-    // few A row-blocks and a contiguous run of B column-blocks in L2.
-    constexpr int kGroupM = 8;
+    // Tile order: groups of `group_m` m-blocks, m fastest inside a group, so the ~148 tiles in flight form a
+    // group_m x (148 / group_m) rectangle of the output: per wave the DRAM side reads group_m A row-blocks and
+    // 148 / group_m B column-blocks.  group_m is chosen by the host to balance the two (gemm_group_m).
+    const int kGroupM = group_m;
     auto tile_coords = [&](int t, int& mb, int& nb) {
         const int per_group = kGroupM * n_tiles;
         const int g = t / per_group;
@@ -428,15 +432,35 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 // ---- host side -------------------------------------------------------------------------------------
 int device_num_sms();
 
+// A wave of `grid` tiles arranged as g m-blocks x (grid / g) n-blocks reads g * kBlockM + (grid / g) * BLOCK_N operand
+// rows of K elements from DRAM (the rest hits L2): minimal for g = sqrt(grid * BLOCK_N / kBlockM), rounded to a power
+// of two and clamped to the matrix.  SOSWSOD_GEMM_GROUP_M (read once) overrides it for experiments.
+static int gemm_group_m(int m_tiles, int n_tiles, int block_n, int grid) {
+    static int forced = -1;
+    if (forced < 0) {
+        const char* e = getenv("SOSWSOD_GEMM_GROUP_M");
+        forced = e ? atoi(e) : 0;
+    }
+    int g = forced;
+    if (g <= 0) {
+        const double ideal = sqrt((double)grid * block_n / kBlockM);
+        g = 1;
+        while (g * 2 <= ideal * 1.2) g *= 2;
+    }
+    if (g > m_tiles) g = m_tiles;
+    return g < 1 ? 1 : g;
+}
+
 template <int BLOCK_N, bool A_MN, bool B_MN, bool OUT_BF16>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, void* d, long long ldd, int m, int n, int k,
                        const GemmEpilogue& ep, unsigned int* sched, cudaStream_t st) {
     auto kern = gemm_bf16_kernel<BLOCK_N, A_MN, B_MN, OUT_BF16>;
     const int smem = gemm_smem_bytes(BLOCK_N);
     SOSWSOD_ENSURE_SMEM(kern, smem);
-    const int tiles = ((m + kBlockM - 1) / kBlockM) * ((n + BLOCK_N - 1) / BLOCK_N);
+    const int m_tiles = (m + kBlockM - 1) / kBlockM, n_tiles = (n + BLOCK_N - 1) / BLOCK_N;
+    const int tiles = m_tiles * n_tiles;
     const int grid = tiles < device_num_sms() ? tiles : device_num_sms();
-    kern<<<grid, kGemmThreads, smem, st>>>(ta, tb, d, ldd, m, n, k, ep, sched);
+    kern<<<grid, kGemmThreads, smem, st>>>(ta, tb, d, ldd, m, n, k, ep, sched, gemm_group_m(m_tiles, n_tiles, BLOCK_N, grid));
     SOSWSOD_CHECK_LAUNCH();
     return SOSWSOD_OK;
 }

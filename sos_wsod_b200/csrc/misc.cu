@@ -21,7 +21,8 @@ constexpr int kTile = 64;
 __global__ void __launch_bounds__(256)
 cast_f32_bf16_kernel(const float* __restrict__ in, long long ld_in, int rows, int cols,
                      const float* __restrict__ col_scale, __nv_bfloat16* __restrict__ out, long long ld_out,
-                     __nv_bfloat16* __restrict__ out_t, long long ld_out_t) {
+                     __nv_bfloat16* __restrict__ out_t, long long ld_out_t,
+                     const __nv_bfloat16* __restrict__ mask_src, long long ld_mask, float mask_scale) {
     __shared__ __nv_bfloat16 tile[kTile][kTile + 2];
     const int r0 = blockIdx.y * kTile, c0 = blockIdx.x * kTile;
     const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;  // 64 x 4
@@ -31,7 +32,10 @@ cast_f32_bf16_kernel(const float* __restrict__ in, long long ld_in, int rows, in
         const int r = r0 + i;
         __nv_bfloat16 v = __float2bfloat16_rn(0.f);
         if (r < rows && c < cols) {
-            v = __float2bfloat16_rn(in[(size_t)r * ld_in + c] * s);
+            float f = in[(size_t)r * ld_in + c] * s;
+            // backward of ReLU (+ dropout): pass the gradient where the saved activation is positive
+            if (mask_src) f *= (__bfloat162float(mask_src[(size_t)r * ld_mask + c]) > 0.f) ? mask_scale : 0.f;
+            v = __float2bfloat16_rn(f);
             if (out) out[(size_t)r * ld_out + c] = v;
         }
         tile[i][tx] = v;
@@ -275,15 +279,17 @@ extern "C" const char* soswsod_last_error(void) { return g_err; }
 
 extern "C" int soswsod_cast_f32_bf16(const float* in, long long ld_in, int rows, int cols, const float* col_scale,
                                      void* out, long long ld_out, void* out_t, long long ld_out_t,
+                                     const void* mask_src, long long ld_mask, float mask_scale,
                                      soswsod_stream_t stream) {
     SOSWSOD_CHECK_ARG(in && (out || out_t), "cast_f32_bf16: null pointer");
     SOSWSOD_CHECK_ARG(rows > 0 && cols > 0 && ld_in >= cols, "cast_f32_bf16: bad shape");
     SOSWSOD_CHECK_ARG(!out || ld_out >= cols, "cast_f32_bf16: ld_out too small");
     SOSWSOD_CHECK_ARG(!out_t || ld_out_t >= rows, "cast_f32_bf16: ld_out_t too small");
+    SOSWSOD_CHECK_ARG(!mask_src || ld_mask >= cols, "cast_f32_bf16: ld_mask too small");
     dim3 grid((cols + kTile - 1) / kTile, (rows + kTile - 1) / kTile);
     cast_f32_bf16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(in, ld_in, rows, cols, col_scale,
                                                                  (__nv_bfloat16*)out, ld_out, (__nv_bfloat16*)out_t,
-                                                                 ld_out_t);
+                                                                 ld_out_t, (const __nv_bfloat16*)mask_src, ld_mask, mask_scale);
     SOSWSOD_CHECK_LAUNCH();
     return SOSWSOD_OK;
 }

@@ -28,15 +28,16 @@ class _LinearAct(Function):
     def backward(ctx, gy):
         xb, wb, y = ctx.saved_tensors
         g = gy.contiguous().float()
-        if ctx.relu:
-            g = g * (y > 0).float() * (1.0 / (1.0 - ctx.p) if ctx.p > 0 else 1.0)
         m, n_out = g.shape
         gbuf = torch.zeros((m, (n_out + 7) // 8 * 8), dtype=torch.bfloat16, device=g.device)  # lda multiple of 8
         gb = gbuf[:, :n_out]
-        ops.cast_f32_bf16(g, out=gb)
+        # ReLU (+ dropout) backward fused into the fp32 -> bf16 cast of the incoming gradient: the saved activation is
+        # positive exactly where the unit was kept and active
+        ops.cast_f32_bf16(g, out=gb, mask_src=y if ctx.relu else None,
+                          mask_scale=(1.0 / (1.0 - ctx.p) if ctx.p > 0 else 1.0))
         gx = ops.gemm_bf16(gb, wb, b_mn=True).to(ctx.x_dtype)
         gw = ops.gemm_bf16(gb, xb, a_mn=True, b_mn=True)
-        gbias = ops.colsum(g) if ctx.has_bias else None
+        gbias = ops.colsum(gb) if ctx.has_bias else None
         return gx, gw, gbias, None, None, None
 
 

@@ -212,9 +212,13 @@ def dropout_mask(m: int, n: int, p: float, seed: int, device="cuda") -> torch.Te
 
 
 def cast_f32_bf16(x: torch.Tensor, col_scale: Optional[torch.Tensor] = None, want_out: bool = True,
-                  want_t: bool = False, out: Optional[torch.Tensor] = None, ld_pad: int = 8):
-    """x fp32 [rows, cols] -> (bf16 [rows, cols] | None, bf16 transposed [cols, rows_padded][:, :rows] | None)."""
-    _need_cuda(x, col_scale)
+                  want_t: bool = False, out: Optional[torch.Tensor] = None, ld_pad: int = 8,
+                  mask_src: Optional[torch.Tensor] = None, mask_scale: float = 1.0):
+    """x fp32 [rows, cols] -> (bf16 [rows, cols] | None, bf16 transposed [cols, rows_padded][:, :rows] | None).
+    mask_src (bf16 [rows, cols]): the result is multiplied by mask_scale where mask_src > 0, by 0 elsewhere."""
+    _need_cuda(x, col_scale, mask_src)
+    if mask_src is not None:
+        assert mask_src.dtype == torch.bfloat16 and mask_src.shape == x.shape and mask_src.stride(1) == 1
     assert x.dtype == torch.float32 and x.dim() == 2 and x.stride(1) == 1
     rows, cols = x.shape
     o = None
@@ -228,6 +232,7 @@ def cast_f32_bf16(x: torch.Tensor, col_scale: Optional[torch.Tensor] = None, wan
         ot = torch.zeros((cols, rp), dtype=torch.bfloat16, device=x.device)[:, :rows]
     check(_lib.load().soswsod_cast_f32_bf16(_ptr(x), x.stride(0), rows, cols, _ptr(col_scale), _ptr(o),
                                             0 if o is None else o.stride(0), _ptr(ot), 0 if ot is None else ot.stride(0),
+                                            _ptr(mask_src), 0 if mask_src is None else mask_src.stride(0), float(mask_scale),
                                             _stream()), "cast_f32_bf16")
     _count(1)
     return o, ot

@@ -452,6 +452,31 @@ def test_multi_input_rcnn_mirror(cuda_lib):
     _, direct = heads([im1, im1f, im2, im2f], [f1, f2], props, [[item["instances1"].to("cuda")], None, None, None])
     for k in losses:
         assert torch.equal(losses[k], direct[k]), k
+    # ... and against the ORACLE (not only against itself): the four views the meta-architecture hands to the head --
+    # [image, flip] per scale through the backbone, proposals per view -- restated for oracle.train_step
+    out = heads.engine().last_output
+    C, K = cfg.MODEL.ROI_HEADS.NUM_CLASSES, cfg.WSL.REFINE_NUM
+    oviews = []
+    for f, keys in ((f1, ("proposals1", "proposals1_flip")), (f2, ("proposals2", "proposals2_flip"))):
+        ft = f["plain5"] if isinstance(f, dict) else f
+        for i, kname in enumerate(keys):
+            pr = item[kname]
+            oviews.append(ref.View(feat=ft[i:i + 1].detach().float().cpu(), boxes=pr.proposal_boxes.tensor.cpu(),
+                                   obj=pr.objectness_logits.cpu(), image_size=pr.image_size))
+    sd = {k: v.detach().float().cpu() for k, v in heads.state_dict().items()}
+    hp = ref.HeadParams(fc1_w=sd["box_head.fc1.weight"], fc1_b=sd["box_head.fc1.bias"], fc2_w=sd["box_head.fc2.weight"],
+                        fc2_b=sd["box_head.fc2.bias"], cls_w=sd["box_predictor.cls.weight"], cls_b=sd["box_predictor.cls.bias"],
+                        det_w=sd["box_predictor.det.weight"], det_b=sd["box_predictor.det.bias"])
+    for k in range(K):
+        hp.refine.append(tuple(sd[f"box_refinery_{k}.{n}"] for n in ("cls_score.weight", "cls_score.bias", "bbox_pred.weight", "bbox_pred.bias")))
+    prev_dev = out.aux["prev"].cpu()
+    exp, oaux = ref.train_step(oviews, item["instances1"].gt_classes, hp, C, K,
+                               prev_override=[prev_dev[0][:, :C]] + [prev_dev[k] for k in range(1, K)])
+    for k, v in exp.items():
+        assert abs(float(direct[k]) - float(v)) < 1e-3, (k, float(direct[k]), float(v))
+    for k in range(K):
+        assert torch.equal(out.aux["gt_class"][k].cpu().long(), oaux["branches"][k]["gt_classes"])
+        assert torch.equal(out.aux["gt_index"][k].cpu().long(), oaux["branches"][k]["gt_index"])
     # inference: one view, post-processed to the dataset's resolution
     model.eval()
     test_item = {"image": item["image2"], "height": 120, "width": 160, "proposals": item["proposals2"]}
