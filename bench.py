@@ -474,12 +474,17 @@ def run_b200_arm(args):
     tot_ms = sum(e[0].elapsed_time(e[1]) for e in gemm_events)
     by_shape = {}
     for e0, e1, fl, shp in gemm_events:
-        d = by_shape.setdefault(shp, [0.0, 0.0, 0])
+        d = by_shape.setdefault(shp, [0.0, 0.0, 0, []])
+        t = e0.elapsed_time(e1)
         d[0] += fl
-        d[1] += e0.elapsed_time(e1)
+        d[1] += t
         d[2] += 1
+        d[3].append(t)
     detail = [{"m": s[0], "n": s[1], "k": s[2], "a_mn": s[3], "b_mn": s[4], "launches": d[2],
-               "avg_ms": d[1] / d[2], "tflops": d[0] / d[1] / 1e9} for s, d in by_shape.items()]
+               "avg_ms": d[1] / d[2], "min_ms": min(d[3]), "max_ms": max(d[3]), "tflops": d[0] / d[1] / 1e9} for s, d in by_shape.items()]
+    # the three fc6-sized GEMMs do the same FLOPs: one of them at > 1.5x the fastest is the "slow mode" of VERDICT r01 weak #1
+    big = [d for d in detail if d["m"] * d["n"] * d["k"] > 5e11]
+    slow_mode = bool(big and max(d["max_ms"] for d in big) > 1.5 * min(d["min_ms"] for d in big))
     fc6 = max(detail, key=lambda d: d["m"] * d["n"] * d["k"] if not d["a_mn"] and not d["b_mn"] else 0)
     achieved = tot_flops / tot_ms / 1e9 if tot_ms > 0 else 0.0
     peak = peaks["bf16_tflops_sustained"]
@@ -492,6 +497,7 @@ def run_b200_arm(args):
         traffic = tj["gemm_bf16_kernel"]["dram_bytes_per_launch_avg"]
         traffic_src = tj["source"]
     alg_bytes = sum((2.0 * (s[0] * s[2] + s[1] * s[2]) + 2.0 * s[0] * s[1]) * d[2] for s, d in by_shape.items()) / max(len(gemm_events), 1)
+    alloc_conf = os.environ.get("PYTORCH_CUDA_ALLOC_CONF", "")
     gemm_ms_per_step = tot_ms / ev_steps
     roofline = {"bound": "tensor", "kernel": f"gemm_bf16_kernel (tcgen05, all {n_gemm} launches of a step)", "achieved": achieved,
                 "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "peak_source": peaks["source"] + ", sustained",
@@ -500,7 +506,7 @@ def run_b200_arm(args):
                 "measured_in": f"a separate untimed pass of {ev_steps} steps with CUDA events around every launch "
                                f"({ev_pass_ms_per_step:.3f} ms/step there)",
                 "gemm_ms_per_step": gemm_ms_per_step, "gemm_share_of_step": gemm_ms_per_step / ev_pass_ms_per_step,
-                "fc6_fwd_tflops": fc6["tflops"], "detail": detail}
+                "fc6_fwd_tflops": fc6["tflops"], "slow_mode_seen_in_event_pass": slow_mode, "detail": detail}
     # ROI pool: per step 2 forward + 2 backward launches (one per scale pair).  Compulsory HBM bytes per step:
     # forward = conv5 planes in + (bf16 operand + uint16 arg-max) out; backward = (bf16 grad + uint16 arg-max) in + fp32 planes out
     plane_bytes = sum(2 * 512 * h * w * 4 for (h, w) in feat_sizes())
@@ -698,6 +704,7 @@ def run_b200_arm(args):
                                         "pooling; small tensors all-reduced" if ex.mode == "sharded" else
                                         "NCCL all-reduce (AVG) per gradient, async, overlapped with the remaining backward"))
                            if ex is not None else "none",
+                           "allocator": alloc_conf or "default",
                            "optimizer": "B200SGD (one fused launch: SGD + momentum 0.9 + weight decay 5e-4, bias lr x2; writes the bf16 GEMM operands)",
                            "fc_flops_per_step": 3 * 2.0 * VIEWS * R_PROPOSALS * (25088 * 4096 + 4096 * 4096)},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches_per_block), "roofline": roofline,
