@@ -1,5 +1,5 @@
 OUT=gpurun_out/r2l; mkdir -p $OUT
-for i in 1 2 3; do
+for i in 1 2; do
   python -m pytest tests/test_gpu_engine.py -m gpu -q -p no:cacheprovider -k "not bench_shape" > /dev/null 2>&1
   for conf in default expandable; do
     if [ $conf = expandable ]; then export PYTORCH_CUDA_ALLOC_CONF=expandable_segments:True; else unset PYTORCH_CUDA_ALLOC_CONF; fi
