@@ -263,9 +263,6 @@ def init_dist(dev):
     # NCCL's INFO lines (the driver counts ranks from them) must not land on stdout, which carries ONE json line
     if os.environ.get("NCCL_DEBUG") and not os.environ.get("NCCL_DEBUG_FILE"):
         os.environ["NCCL_DEBUG_FILE"] = "/dev/stderr"
-    # every async collective of the exchange is waited for before its tensors are released: the process group can hold
-    # references instead of record_stream()-ing them (which delays the caching allocator's reuse of the 411 MB blocks)
-    os.environ.setdefault("TORCH_NCCL_AVOID_RECORD_STREAMS", "1")
     # ... and its version banner is printed with a bare printf: point fd 1 at stderr while the communicator comes up
     sys.stdout.flush()
     saved = os.dup(1)

@@ -17,7 +17,11 @@ Two modes behind one object, both giving every rank the SAME fp32 result as DDP'
                all-reduced.
 
 Every collective is issued with async_op=True from the stream that produced its input; `Work.wait()` orders the
-consumer's stream behind it -- no host synchronisation anywhere.  Backends without reduce_scatter_tensor / AVG (gloo,
+consumer's stream behind it -- no host synchronisation anywhere.  The consumer is the exchange's UPDATE STREAM
+(`update_stream()`): solver.B200SGD queues "wait for the collectives -> fused SGD on the owned rows -> operand
+all-gather" there, so the compute stream goes straight on to the next step's ROI pooling (which reads no weights) and
+only waits at `operand_gate()`, right before its first GEMM.  The engine produces fc1.weight's gradient LAST in the
+backward, which puts the tail of the exchange + update + all-gather under that pooling instead of in front of it.  Backends without reduce_scatter_tensor / AVG (gloo,
 used by the CPU tests of this host logic) take an all-reduce based path with the same result."""
 from __future__ import annotations
 
@@ -52,6 +56,12 @@ class GradientExchange:
         self._rs: List[Tuple[str, torch.Tensor, int, object]] = []     # (key, panel, row0, work) reduce-scatters of this step
         self._gather: List = []                        # operand all-gathers still in flight
         self.master_stale = False
+        self._update_stream = None
+        self._update_done = None                       # event on the update stream: this step's parameter update is queued
+        # True: `backward()` returns without ordering the compute stream behind the collectives -- the attached optimizer
+        # consumes the gradients on the update stream.  False: DDP's contract (gradients are final when backward returns).
+        self.lazy_wait = False
+        self._expected_ptrs: Dict[str, int] = {}
         self._layout: Dict[str, List[Tuple[int, int]]] = {}
         self.bytes_last_step = {"reduce_scatter": 0, "all_reduce": 0, "all_gather": 0}
 
@@ -88,11 +98,15 @@ class GradientExchange:
                 w = dist.all_reduce(grad, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
             self._works.append(w)
 
-    def wait_gradients(self) -> None:
-        """Orders the current stream behind every gradient collective of this step."""
+    def wait_allreduces(self) -> None:
+        """Orders the current stream behind the all-reduces of this step (the small tensors; in "allreduce" mode all)."""
         for w in self._works:
             w.wait()
         self._works.clear()
+
+    def wait_gradients(self) -> None:
+        """Orders the current stream behind every gradient collective of this step."""
+        self.wait_allreduces()
         for _, _, _, w in self._rs:
             w.wait()
 
@@ -132,8 +146,34 @@ class GradientExchange:
             self._layout = lay
         self._rs.clear()
 
+    def update_stream(self):
+        if self._update_stream is None:
+            self._update_stream = torch.cuda.Stream(device=next(iter(self.master.values())).device)
+        return self._update_stream
+
+    def mark_update_done(self) -> None:
+        """Called on the update stream after the optimizer's launch (and the operand all-gathers) are queued."""
+        self._update_done = torch.cuda.Event()
+        self._update_done.record()
+
+    def expect_gradient_buffers(self, ptrs: Dict[str, int]) -> None:
+        """The storage addresses of the gradient tensors the collectives of this step work on (in place)."""
+        self._expected_ptrs = dict(ptrs)
+
+    def check_gradient_buffer(self, key: str, grad: torch.Tensor) -> None:
+        """The optimizer's `.grad` must BE the buffer the collective reduced in place; if autograd had to clone it (a
+        second reference was alive) the clone holds this rank's un-averaged values."""
+        want = self._expected_ptrs.get(key)
+        if want is not None and grad.data_ptr() != want:
+            raise RuntimeError(f"GradientExchange: the gradient of {key} is not the buffer the collective reduced (autograd "
+                               "cloned it: something else held a reference to the step's gradient tensors)")
+
     def operand_gate(self) -> None:
-        """engine.operand_gate: the current stream waits for the operand all-gathers before the first GEMM reads them."""
+        """engine.operand_gate: the current stream waits for the parameter update and the operand all-gathers before
+        the first GEMM reads the weights."""
+        if self._update_done is not None:
+            torch.cuda.current_stream().wait_event(self._update_done)
+            self._update_done = None
         for w in self._gather:
             w.wait()
         self._gather.clear()

@@ -319,30 +319,11 @@ class OICRPlusHeadEngine:
             grad_hook("fc2_w", dW7, 0)
             grad_hook("fc2_b", db7, 0)
         dH6 = ops.gemm_bf16(dH7, op.w7, b_mn=True, out_dtype=torch.bfloat16, mask_src=H6, mask_scale=mscale)
-        panels = self.fc1_wgrad_panels if grad_hook is not None else 1
-        if panels > 1 and cfg.fc_dim % (128 * panels) == 0:
-            # data-parallel: fc6's weight gradient (411 MB, 85 % of the exchanged bytes) is produced in row panels and
-            # every panel's collective starts as soon as its GEMM is queued, so the exchange overlaps the remaining
-            # panels, the fc6 dgrad and the ROI backward instead of starting only after the whole 1.2 ms GEMM.  A
-            # panel = the same tiles the single launch would compute (bit-identical result).
-            dW6 = grad_buf("fc1_w", (cfg.fc_dim, cfg.in_dim))
-            if dW6 is None:
-                dW6 = torch.empty((cfg.fc_dim, cfg.in_dim), dtype=torch.float32, device=dev)
-            rows = cfg.fc_dim // panels
-            for pi in range(panels):
-                m0 = pi * rows
-                ops.gemm_bf16(dH6[:, m0:m0 + rows], X, a_mn=True, b_mn=True, out=dW6[m0:m0 + rows])
-                grad_hook("fc1_w", dW6[m0:m0 + rows], m0)
-            db6 = ops.colsum(dH6)
-            grad_hook("fc1_b", db6, 0)
-            self.launches_last_step += panels - 1
-        else:
-            dW6 = ops.gemm_bf16(dH6, X, a_mn=True, b_mn=True, out=grad_buf("fc1_w", (cfg.fc_dim, cfg.in_dim)))
-            db6 = bias_grad(dH6)
-            if grad_hook is not None:
-                grad_hook("fc1_w", dW6, 0)
-                grad_hook("fc1_b", db6, 0)
-        self.launches_last_step += 9
+        # fc6: input gradient and ROI backward FIRST, weight gradient LAST.  With a gradient hook (data-parallel) fc6's
+        # weight gradient is 85 % of the exchanged bytes: produced last, its collectives run behind nothing but their own
+        # later panels -- not under the ROI backward, whose one-CTA-per-SM kernel loses a whole wave when NCCL's CTAs sit
+        # on its SMs (+0.2 ms at 8 GPUs) -- and the tail of the exchange, the sharded update and the operand all-gather
+        # slide under the NEXT step's ROI forward (solver.B200SGD runs them on the exchange's update stream).
         grad_feats: List[torch.Tensor] = []
         if need_feat_grad:
             dX = ops.gemm_bf16(dH6, op.w6, b_mn=True, out_dtype=torch.bfloat16)
@@ -355,6 +336,29 @@ class OICRPlusHeadEngine:
                                                         spatial_scale=cfg.spatial_scale, plan=plan))
                 row += m
                 self.launches_last_step += 1
+            del dX
+        panels = self.fc1_wgrad_panels if grad_hook is not None else 1
+        if panels > 1 and cfg.fc_dim % (128 * panels) == 0:
+            # row panels: every panel's collective starts as soon as its GEMM is queued and overlaps the remaining panels.
+            # A panel = the same tiles the single launch would compute (bit-identical result).
+            dW6 = grad_buf("fc1_w", (cfg.fc_dim, cfg.in_dim))
+            if dW6 is None:
+                dW6 = torch.empty((cfg.fc_dim, cfg.in_dim), dtype=torch.float32, device=dev)
+            db6 = ops.colsum(dH6)
+            grad_hook("fc1_b", db6, 0)
+            rows = cfg.fc_dim // panels
+            for pi in range(panels):
+                m0 = pi * rows
+                ops.gemm_bf16(dH6[:, m0:m0 + rows], X, a_mn=True, b_mn=True, out=dW6[m0:m0 + rows])
+                grad_hook("fc1_w", dW6[m0:m0 + rows], m0)
+            self.launches_last_step += panels - 1
+        else:
+            dW6 = ops.gemm_bf16(dH6, X, a_mn=True, b_mn=True, out=grad_buf("fc1_w", (cfg.fc_dim, cfg.in_dim)))
+            db6 = bias_grad(dH6)
+            if grad_hook is not None:
+                grad_hook("fc1_b", db6, 0)
+                grad_hook("fc1_w", dW6, 0)
+        self.launches_last_step += 9
         if side is not None:
             torch.cuda.current_stream().wait_stream(side)
         if grad_hook is None:

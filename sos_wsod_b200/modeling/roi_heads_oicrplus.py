@@ -65,10 +65,17 @@ class _FusedHeadStep(Function):
         if out is None:
             raise RuntimeError("OICRPlusHeads: backward ran twice through one fused head step (retain_graph=True / a second "
                                ".backward()); the step hands its gradient buffers to autograd once -- run forward again")
-        if ctx.exchange is not None:
-            # the gradient collectives started from the engine's hook run on NCCL's stream: order this stream behind
-            # them BEFORE autograd touches the buffers (AccumulateGrad adopts them, or clones them when it cannot)
-            ctx.exchange.wait_gradients()
+        if ctx.exchange is not None and ctx.exchange.world > 1:
+            # The gradient collectives started from the engine's hook run on NCCL's stream.  DDP's contract: order this
+            # stream behind them before autograd touches the buffers.  With an attached B200SGD (lazy_wait) the optimizer
+            # consumes them on the exchange's update stream instead, and checks that `.grad` IS the reduced buffer.
+            if ctx.exchange.lazy_wait:
+                # the all-reduced tensors (biases, the fused head block whose row slices autograd may clone) are final
+                # when backward returns; the reduce-scattered matrices stay with the update stream
+                ctx.exchange.wait_allreduces()
+            else:
+                ctx.exchange.wait_gradients()
+            ctx.exchange.expect_gradient_buffers({k: out.grads[k].data_ptr() for k in ctx.exchange.sharded})
         gs = torch.stack([x.reshape(()) for x in gouts])
         pre = ctx.loss_scale        # the gradients were produced for pre * sum(losses) (heads.expected_loss_scale)
         if ctx.deferred is not None:

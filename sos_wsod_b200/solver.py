@@ -8,6 +8,7 @@ and writes p, buf) instead of torch's 3-4 elementwise passes per tensor, and -- 
 the head's bf16 GEMM operands in the same pass.  Gradient clipping (SOLVER.CLIP_GRADIENTS) is off in every released OICR+ config and not built."""
 from __future__ import annotations
 
+import contextlib
 from typing import Any, Dict, List, Set
 
 import torch
@@ -69,8 +70,12 @@ class B200SGD(torch.optim.Optimizer):
         self.launches_last_step = 0
 
     def attach_head(self, heads) -> "B200SGD":
-        """heads: an OICRPlusHeads whose parameters this optimizer updates."""
+        """heads: an OICRPlusHeads whose parameters this optimizer updates.  If the head exchanges its gradients
+        (set_gradient_exchange) this optimizer becomes their consumer: backward() no longer blocks the compute stream."""
         self._heads.append(heads)
+        ex = getattr(heads, "exchange", None)
+        if ex is not None:
+            ex.lazy_wait = True
         return self
 
     def sync_state(self) -> None:
@@ -100,46 +105,62 @@ class B200SGD(torch.optim.Optimizer):
                 loss = closure()
         sinks = self._sinks()
         self.launches_last_step = 0
-        # data-parallel heads: finish the gradient exchange; a sharded parameter is updated only on the rows this rank
-        # owns (their averaged gradient arrived by reduce-scatter), its bf16 operand rows are all-gathered afterwards
-        shard_rows = {}
+        # Data-parallel heads: the rest of the exchange runs on the exchange's UPDATE STREAM -- wait for the gradient
+        # collectives, update (a sharded parameter only on the rows this rank owns: their averaged gradient arrived by
+        # reduce-scatter), all-gather the bf16 operand rows -- while the compute stream goes on to the next step's ROI
+        # pooling and waits at the engine's operand gate, right before its first GEMM.
+        shard_rows, exchanges, key_of = {}, [], {}
         for h in self._heads:
             ex = getattr(h, "exchange", None)
             if ex is not None and ex.world > 1:
+                exchanges.append((h, ex))
+                for key, prm in ex.master.items():
+                    key_of[id(prm)] = (ex, key)
+        update_stream = exchanges[0][1].update_stream() if exchanges else None
+        if update_stream is not None:
+            ready = torch.cuda.Event()
+            ready.record()                       # every gradient kernel of the step is queued behind this point
+            update_stream.wait_event(ready)
+        ctx = torch.cuda.stream(update_stream) if update_stream is not None else contextlib.nullcontext()
+        with ctx:
+            for h, ex in exchanges:
                 ex.wait_gradients()
                 for key in sorted(ex.sharded):
                     shard_rows[id(ex.master[key])] = ex.owned_rows(key)
-        by_momentum, touched = {}, []          # the reference makes one group per parameter: batch across groups
-        for group in self.param_groups:
-            for p in group["params"]:
-                if p.grad is None:
-                    continue
-                if not p.is_cuda:
-                    raise RuntimeError("B200SGD steps CUDA parameters only (sm_100a kernel); there is no CPU fallback")
-                st = self.state[p]
-                if "momentum_buffer" not in st:
-                    st["momentum_buffer"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
-                grad = p.grad if p.grad.is_contiguous() else p.grad.contiguous()
-                if not p.is_contiguous():
-                    raise RuntimeError("B200SGD needs contiguous parameters")
-                ob, of = sinks.get(id(p), (None, None))
-                items = by_momentum.setdefault(float(group["momentum"]), [])
-                pd, buf = p.detach(), st["momentum_buffer"]
-                for lo, hi in shard_rows.get(id(p), [(0, p.size(0) if p.dim() else 1)]):
-                    whole = (lo == 0 and hi == (p.size(0) if p.dim() else 1))
-                    sl = (lambda t: t) if whole else (lambda t, lo=lo, hi=hi: None if t is None else t[lo:hi])
-                    items.append((sl(pd), sl(grad), sl(buf), group["lr"], group["weight_decay"], sl(ob), sl(of)))
-                touched.append(p)
-        for momentum, items in by_momentum.items():
-            self.launches_last_step += ops.sgd_multi(items, momentum)
+            by_momentum, touched = {}, []          # the reference makes one group per parameter: batch across groups
+            for group in self.param_groups:
+                for p in group["params"]:
+                    if p.grad is None:
+                        continue
+                    if not p.is_cuda:
+                        raise RuntimeError("B200SGD steps CUDA parameters only (sm_100a kernel); there is no CPU fallback")
+                    st = self.state[p]
+                    if "momentum_buffer" not in st:
+                        st["momentum_buffer"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
+                    grad = p.grad if p.grad.is_contiguous() else p.grad.contiguous()
+                    if not p.is_contiguous():
+                        raise RuntimeError("B200SGD needs contiguous parameters")
+                    if id(p) in key_of:
+                        key_of[id(p)][0].check_gradient_buffer(key_of[id(p)][1], p.grad)
+                    if update_stream is not None:
+                        grad.record_stream(update_stream)     # `.grad` may be dropped by the host before the update ran
+                    ob, of = sinks.get(id(p), (None, None))
+                    items = by_momentum.setdefault(float(group["momentum"]), [])
+                    pd, buf = p.detach(), st["momentum_buffer"]
+                    for lo, hi in shard_rows.get(id(p), [(0, p.size(0) if p.dim() else 1)]):
+                        whole = (lo == 0 and hi == (p.size(0) if p.dim() else 1))
+                        sl = (lambda t: t) if whole else (lambda t, lo=lo, hi=hi: None if t is None else t[lo:hi])
+                        items.append((sl(pd), sl(grad), sl(buf), group["lr"], group["weight_decay"], sl(ob), sl(of)))
+                    touched.append(p)
+            for momentum, items in by_momentum.items():
+                self.launches_last_step += ops.sgd_multi(items, momentum)
+            for h, ex in exchanges:
+                op = h.engine().op
+                ex.gather_operands({"fc1_w": op.w6, "fc2_w": op.w7})
+                ex.mark_update_done()
         for p in touched:
             # the kernel wrote through raw pointers: bump the version counters like an in-place op would
             torch.autograd.graph.increment_version(p)
-        for h in self._heads:
-            ex = getattr(h, "exchange", None)
-            if ex is not None and ex.world > 1:
-                op = h.engine().op
-                ex.gather_operands({"fc1_w": op.w6, "fc2_w": op.w7})
         for h in self._heads:
             op = h.engine().op
             if all(p.grad is not None for p in op.master.values()):
