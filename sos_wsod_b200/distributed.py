@@ -77,6 +77,11 @@ class GradientExchange:
         """The engine's grad_hook: starts the collective of one gradient (or one row panel of fc1.weight)."""
         if self.world == 1:
             return
+        # Work on an independent tensor over the same storage: a reference to `grad` itself (or to a view of it, which
+        # keeps its base alive) held by this object or by the process group would make autograd's AccumulateGrad CLONE the
+        # gradient instead of adopting the buffer -- and the clone would be taken before the collective has run.
+        grad = torch.empty(0, dtype=grad.dtype, device=grad.device).set_(grad.untyped_storage(), grad.storage_offset(),
+                                                                        grad.shape, grad.stride())
         if key in self.sharded:
             rows = grad.size(0)
             if rows % self.world != 0:
