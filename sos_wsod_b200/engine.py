@@ -180,6 +180,7 @@ class OICRPlusHeadEngine:
         self.last_output: Optional[TrainOutput] = None
         self.fc1_wgrad_panels = 4          # only with a grad_hook (data-parallel): see train_step
         self.operand_gate = None           # callable: makes the current stream wait for in-flight operand updates
+        self.fc1_wgrad_position = "first"  # "first" | "middle" | "last" among (dW6, dX, ROI backward); see train_step
         self.bias_on_side_stream = True    # bias-gradient column sums under the GEMMs (only without a grad_hook)
         # engine-level training loops may let the step write the big weight gradients into the same buffers every
         # step (the caller consumes them before the next step); never with autograd, which adopts the buffers as .grad
@@ -319,15 +320,15 @@ class OICRPlusHeadEngine:
             grad_hook("fc2_w", dW7, 0)
             grad_hook("fc2_b", db7, 0)
         dH6 = ops.gemm_bf16(dH7, op.w7, b_mn=True, out_dtype=torch.bfloat16, mask_src=H6, mask_scale=mscale)
-        # fc6: input gradient and ROI backward FIRST, weight gradient LAST.  With a gradient hook (data-parallel) fc6's
-        # weight gradient is 85 % of the exchanged bytes: produced last, its collectives run behind nothing but their own
-        # later panels -- not under the ROI backward, whose one-CTA-per-SM kernel loses a whole wave when NCCL's CTAs sit
-        # on its SMs (+0.2 ms at 8 GPUs) -- and the tail of the exchange, the sharded update and the operand all-gather
-        # slide under the NEXT step's ROI forward (solver.B200SGD runs them on the exchange's update stream).
+        # fc6: weight gradient (dW6, in row panels with a gradient hook), input gradient (dX) and the ROI backward.  The
+        # order only matters data-parallel, where dW6 is 85 % of the exchanged bytes and its collectives share SMs / HBM
+        # with whatever runs next; `fc1_wgrad_position` places the panels first / between dX and the ROI backward / last.
         grad_feats: List[torch.Tensor] = []
-        if need_feat_grad:
-            dX = ops.gemm_bf16(dH6, op.w6, b_mn=True, out_dtype=torch.bfloat16)
-            self.launches_last_step += 1
+
+        def input_gradient():
+            return ops.gemm_bf16(dH6, op.w6, b_mn=True, out_dtype=torch.bfloat16)
+
+        def roi_backward(dX):
             row = 0
             for f, r, (am, plan) in zip(vb.feats, vb.rois, argmaxes):
                 m = r.size(0)
@@ -336,28 +337,43 @@ class OICRPlusHeadEngine:
                                                         spatial_scale=cfg.spatial_scale, plan=plan))
                 row += m
                 self.launches_last_step += 1
-            del dX
-        panels = self.fc1_wgrad_panels if grad_hook is not None else 1
-        if panels > 1 and cfg.fc_dim % (128 * panels) == 0:
-            # row panels: every panel's collective starts as soon as its GEMM is queued and overlaps the remaining panels.
-            # A panel = the same tiles the single launch would compute (bit-identical result).
-            dW6 = grad_buf("fc1_w", (cfg.fc_dim, cfg.in_dim))
-            if dW6 is None:
-                dW6 = torch.empty((cfg.fc_dim, cfg.in_dim), dtype=torch.float32, device=dev)
-            db6 = ops.colsum(dH6)
-            grad_hook("fc1_b", db6, 0)
-            rows = cfg.fc_dim // panels
-            for pi in range(panels):
-                m0 = pi * rows
-                ops.gemm_bf16(dH6[:, m0:m0 + rows], X, a_mn=True, b_mn=True, out=dW6[m0:m0 + rows])
-                grad_hook("fc1_w", dW6[m0:m0 + rows], m0)
-            self.launches_last_step += panels - 1
-        else:
-            dW6 = ops.gemm_bf16(dH6, X, a_mn=True, b_mn=True, out=grad_buf("fc1_w", (cfg.fc_dim, cfg.in_dim)))
-            db6 = bias_grad(dH6)
-            if grad_hook is not None:
+
+        def weight_gradient():
+            panels = self.fc1_wgrad_panels if grad_hook is not None else 1
+            if panels > 1 and cfg.fc_dim % (128 * panels) == 0:
+                # row panels: every panel's collective starts as soon as its GEMM is queued and overlaps what follows.
+                # A panel = the same tiles the single launch would compute (bit-identical result).
+                dW6 = grad_buf("fc1_w", (cfg.fc_dim, cfg.in_dim))
+                if dW6 is None:
+                    dW6 = torch.empty((cfg.fc_dim, cfg.in_dim), dtype=torch.float32, device=dev)
+                db6 = ops.colsum(dH6)
                 grad_hook("fc1_b", db6, 0)
-                grad_hook("fc1_w", dW6, 0)
+                rows = cfg.fc_dim // panels
+                for pi in range(panels):
+                    m0 = pi * rows
+                    ops.gemm_bf16(dH6[:, m0:m0 + rows], X, a_mn=True, b_mn=True, out=dW6[m0:m0 + rows])
+                    grad_hook("fc1_w", dW6[m0:m0 + rows], m0)
+                self.launches_last_step += panels - 1
+            else:
+                dW6 = ops.gemm_bf16(dH6, X, a_mn=True, b_mn=True, out=grad_buf("fc1_w", (cfg.fc_dim, cfg.in_dim)))
+                db6 = bias_grad(dH6)
+                if grad_hook is not None:
+                    grad_hook("fc1_b", db6, 0)
+                    grad_hook("fc1_w", dW6, 0)
+            return dW6, db6
+
+        pos = self.fc1_wgrad_position if need_feat_grad else "first"
+        if pos == "first":
+            dW6, db6 = weight_gradient()
+        if need_feat_grad:
+            dX = input_gradient()
+            self.launches_last_step += 1
+            if pos == "middle":
+                dW6, db6 = weight_gradient()
+            roi_backward(dX)
+            del dX
+            if pos == "last":
+                dW6, db6 = weight_gradient()
         self.launches_last_step += 9
         if side is not None:
             torch.cuda.current_stream().wait_stream(side)

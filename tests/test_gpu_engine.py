@@ -385,7 +385,13 @@ def test_grad_hook_panels_are_bit_identical(cuda_lib):
     out = eng.train_step(vb, gt_int, grad_hook=hook)
     for k in ref_out.grads:
         assert torch.equal(ref_out.grads[k], out.grads[k]), k
-    assert [s[0] for s in seen] == ["head_w", "head_b", "fc2_w", "fc2_b", "fc1_b"] + ["fc1_w"] * 4   # fc6's weight gradient last
+    assert [s[0] for s in seen] == ["head_w", "head_b", "fc2_w", "fc2_b", "fc1_b"] + ["fc1_w"] * 4
+    for pos in ("middle", "last"):      # the panels' place among (dW6, dX, ROI backward) changes no value
+        eng.fc1_wgrad_position = pos
+        o2 = eng.train_step(vb, gt_int, grad_hook=lambda *a: None)
+        assert all(torch.equal(ref_out.grads[k], o2.grads[k]) for k in ref_out.grads)
+        assert all(torch.equal(a, b) for a, b in zip(ref_out.grad_feats, o2.grad_feats))
+    eng.fc1_wgrad_position = "first"
     rows = cfg.fc_dim // 4
     assert [s[3] for s in seen if s[0] == "fc1_w"] == [0, rows, 2 * rows, 3 * rows]
     assert sum(s[2] for s in seen if s[0] == "fc1_w") == out.grads["fc1_w"].numel()
