@@ -302,7 +302,20 @@ def run_b200_arm(args):
 
     heads, cfg = build_heads(dev)
     eng = heads.engine()
-    ex = heads.set_gradient_exchange(mode=args.exchange) if world > 1 else None
+    ex = None
+    if world > 1:
+        mode = args.exchange
+        if mode == "auto":
+            try:
+                ex = heads.set_gradient_exchange(mode="nvls")
+            except Exception as e:      # no multicast / symmetric memory on this platform
+                sys.stderr.write(f"[bench] nvls exchange unavailable ({type(e).__name__}: {e}); using sharded\n")
+                heads.exchange = None
+                heads.grad_hook = None
+                heads._engine = None
+                ex = heads.set_gradient_exchange(mode="sharded")
+        else:
+            ex = heads.set_gradient_exchange(mode=mode)
     eng = heads.engine()
     opt = build_optimizer(cfg, heads)
     master = eng.op.master
@@ -550,7 +563,7 @@ def run_b200_arm(args):
     roofline["roi_pool"] = roi
     n_params = sum(p.numel() for p in master.values())
     sgd_ms = sum(e0.elapsed_time(e1) for e0, e1 in sgd_events) / ev_steps
-    shard = (1.0 / world) if (ex is not None and ex.mode == "sharded") else 1.0
+    shard = (1.0 / world) if (ex is not None and ex.mode in ("sharded", "nvls")) else 1.0
     sgd_bytes = n_params * shard * (12 + 8 + 2)        # p, grad, buf read; p, buf written; bf16 operand written
     roofline["sgd_step"] = {"ms_per_step": sgd_ms, "launches_per_step": len(sgd_events) // ev_steps, "bytes": sgd_bytes,
                             "hbm_gbs": sgd_bytes / (sgd_ms * 1e-3) / 1e9 if sgd_ms > 0 else 0.0,
@@ -559,7 +572,28 @@ def run_b200_arm(args):
 
     # ---- N > 1: the exchange gives every rank the mean of the ranks' gradients (checked outside any timed region) ----
     exchange_check = None
-    if ex is not None:
+    if ex is not None and ex.mode == "nvls":
+        # the fused update reduces, updates and broadcasts in one kernel: check its RESULT after the steps above -- every
+        # rank must hold bit-identical bf16 operands, equal to the cast of the fp32 rows it owns (the full N-rank proof
+        # against all-reduce + torch.optim.SGD is scripts/check_exchange.py, results under profiles/)
+        ex.operand_gate()
+        torch.cuda.synchronize()
+        op = eng.op
+        sums = torch.stack([op.w6.view(torch.int16).to(torch.int64).sum(), op.w7.view(torch.int16).to(torch.int64).sum()])
+        allsums = [torch.empty_like(sums) for _ in range(world)]
+        dist.all_gather(allsums, sums)
+        same = all(bool(torch.equal(a, allsums[0])) for a in allsums)
+        own_ok = True
+        for key, opnd in (("fc1_w", op.w6), ("fc2_w", op.w7)):
+            lo, hi = ex.owned_rows_nvls(key)
+            own_ok = own_ok and bool(torch.equal(opnd[lo:hi], master[key].detach()[lo:hi].to(torch.bfloat16)))
+        flag = torch.tensor([int(own_ok)], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        exchange_check = {"mode": "nvls", "bf16_operands_bit_identical_on_all_ranks": same,
+                          "owned_rows_equal_cast_of_fp32_masters_on_every_rank": bool(flag.item()), "ok": bool(same and flag.item()),
+                          "bytes_per_rank_per_step": dict(ex.bytes_last_step),
+                          "full_check": "scripts/check_exchange.py nvls (vs all-reduce(AVG) + torch.optim.SGD, 3 steps)"}
+    elif ex is not None:
         im = dev_imgs[0]
         vb = ViewBatch(im["feats"], im["rois"], im["obj"], R_PROPOSALS)
         eng.op.refresh(force=False)
@@ -716,10 +750,16 @@ def run_b200_arm(args):
                            "timing": f"median of {n_blocks} blocks of exactly {K_steps} steps (CUDA events, max over ranks per block)",
                            "extra_untimed_warmup_steps": PRE_WARMUP + 3 * settle_blocks,
                            "extra_untimed_warmup_steps_e2e": 3 * settle_blocks_e2e,
-                           "exchange": (f"{ex.mode}: " + ("reduce-scatter fp32 grads of fc1/fc2 weights (per fc1 row panel, started behind "
-                                        "its GEMM) -> SGD on the owned rows -> all-gather bf16 operands behind the next step's ROI "
-                                        "pooling; small tensors all-reduced" if ex.mode == "sharded" else
-                                        "NCCL all-reduce (AVG) per gradient, async, overlapped with the remaining backward"))
+                           "exchange": (f"{ex.mode}: " + {
+                               "nvls": "fc1/fc2 weight gradients and bf16 operands in symmetric NVSwitch-multicast memory; ONE kernel per "
+                                       "rank (soswsod_sgd_nvls) reads the ranks' gradient sum of its rows through the switch "
+                                       "(multimem.ld_reduce), applies SGD and broadcasts the refreshed operand rows (multimem.st), "
+                                       "bracketed by two cross-rank barriers, on an update stream behind the next step's ROI pooling; "
+                                       "small tensors all-reduced (NCCL)",
+                               "sharded": "reduce-scatter fp32 grads of fc1/fc2 weights (per fc1 row panel, started behind its GEMM) -> SGD on "
+                                          "the owned rows -> all-gather bf16 operands, on an update stream behind the next step's ROI "
+                                          "pooling; small tensors all-reduced",
+                               "allreduce": "NCCL all-reduce (AVG) per gradient, async, overlapped with the remaining backward"}[ex.mode])
                            if ex is not None else "none",
                            "allocator": alloc_conf or "default",
                            "optimizer": "B200SGD (one fused launch: SGD + momentum 0.9 + weight decay 5e-4, bias lr x2; writes the bf16 GEMM operands)",
@@ -986,8 +1026,10 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="train", choices=["train", "detect"],
                     help="train = BASELINE configs[1] (the bench line; configs[3] with --shape coco); detect = configs[4]")
-    ap.add_argument("--exchange", default="sharded", choices=["sharded", "allreduce"],
-                    help="N > 1: reduce-scatter + sharded SGD + bf16 operand all-gather, or DDP-style all-reduce")
+    ap.add_argument("--exchange", default="auto", choices=["auto", "nvls", "sharded", "allreduce"],
+                    help="N > 1: nvls = fused reduce + SGD + operand broadcast kernel over NVSwitch multicast memory; sharded = "
+                         "NCCL reduce-scatter + owned-row SGD + bf16 operand all-gather; allreduce = DDP's arithmetic; "
+                         "auto = nvls where the platform offers multicast, else sharded")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--shape", default="voc", choices=["voc", "coco"],
                     help="voc = BASELINE configs[1] (the bench line); coco = configs[3] (80 classes)")

@@ -32,13 +32,16 @@ def main():
         assert torch.equal(pa, pb)
     a.set_gradient_exchange(mode=mode)
     opt_a = build_optimizer(cfg, a)
+    if os.environ.get("CHECK_SYNC_EACH_STEP"):
+        print("synchronising the device after every optimizer step (serialised pipeline)", file=sys.stderr)
     opt_b = torch.optim.SGD(get_optimizer_param_groups(cfg, b), cfg.SOLVER.BASE_LR, momentum=cfg.SOLVER.MOMENTUM)
     lr_boost = 50.0                            # make three steps move the weights visibly
     for o in (opt_a, opt_b):
         for g in o.param_groups:
             g["lr"] *= lr_boost
     sizes = [(480, 640), (576, 768)]
-    for step in range(3):
+    n_steps = int(os.environ.get("CHECK_STEPS", "1"))      # 1: identical weights on both paths (no chaotic feedback)
+    for step in range(n_steps):
         views, gt = training_image(step, rank, R=R, sizes=sizes, num_classes=bench.NUM_CLASSES)
         feats, rois, obj = pack_views(views)
         feats = [f.to(dev) for f in feats]
@@ -53,6 +56,8 @@ def main():
                 for p in heads.parameters():
                     dist.all_reduce(p.grad, op=dist.ReduceOp.AVG)
             opt.step()
+            if os.environ.get("CHECK_SYNC_EACH_STEP"):
+                torch.cuda.synchronize()
     sd_a = a.state_dict()                       # collective: brings the rows owned by other ranks up to date
     opt_a.sync_state()
     errs = {}
@@ -79,7 +84,7 @@ def main():
     ok = torch.tensor([int(opnd_ok)], device=dev)
     dist.all_reduce(ok, op=dist.ReduceOp.MIN)
     if rank == 0:
-        print(json.dumps({"check": "exchange + B200SGD vs all-reduce(AVG) + torch.optim.SGD, 3 steps", "mode": mode, "n_gpus": world,
+        print(json.dumps({"check": f"exchange + B200SGD vs all-reduce(AVG) + torch.optim.SGD, {n_steps} step(s)", "mode": mode, "n_gpus": world,
                           "max_rel_err_params": float(worst[0]), "max_rel_err_momentum": float(worst[1]),
                           "bf16_operands_equal_cast_of_masters_on_every_rank": bool(ok.item()),
                           "fc1_weight_moved_by": moved, "rank0_param_errs": {k: float(f"{v:.3g}") for k, v in errs.items()},

@@ -236,9 +236,96 @@ sgd_multi_kernel(const __grid_constant__ SgdBatch b) {
     }
 }
 
+// The data-parallel update as ONE kernel over NVSwitch multicast memory (the fused compute + collective of this path):
+// every rank owns a block of rows of the big weight matrices.  For its rows it
+//   * reads the SUM over all ranks of the gradient with multimem.ld_reduce (the switch adds the ranks' copies: the
+//     reduce-scatter, with no ring and no staging buffer),
+//   * applies SGD + momentum + weight decay to its rows of the fp32 master and momentum buffer (local memory),
+//   * writes the refreshed bf16 GEMM-operand rows with multimem.st, which lands them in EVERY rank's operand matrix (the
+//     all-gather).
+// grad_mc / out_bf16_mc are multicast addresses of symmetric buffers (same offset on every rank); the caller brackets
+// the launch with cross-rank barriers (all gradients written before, all operand rows landed after).
+struct SgdNvlsBatch {
+    soswsod_sgd_nvls_tensor t[SOSWSOD_SGD_NVLS_MAX_TENSORS];
+    int block_start[SOSWSOD_SGD_NVLS_MAX_TENSORS + 1];
+    int count;
+    float momentum, gscale;
+};
+
+__global__ void __launch_bounds__(256)
+sgd_nvls_kernel(const __grid_constant__ SgdNvlsBatch b) {
+    int ti = 0;
+    while (ti + 1 < b.count && (int)blockIdx.x >= b.block_start[ti + 1]) ++ti;
+    const soswsod_sgd_nvls_tensor& t = b.t[ti];
+    const long long e0 = (long long)((int)blockIdx.x - b.block_start[ti]) * kSgdBlockElems;
+    const long long e1 = e0 + kSgdBlockElems < t.n ? e0 + kSgdBlockElems : t.n;
+    float* __restrict__ p = t.param;
+    float* __restrict__ mb = t.momentum_buf;
+    const float* g_mc = t.grad_mc;
+    __nv_bfloat16* ob_mc = reinterpret_cast<__nv_bfloat16*>(t.out_bf16_mc);
+    const float lr = t.lr, wd = t.weight_decay, mom = b.momentum, gs = b.gscale;
+    for (long long i = e0 + 8LL * threadIdx.x; i + 8 <= e1; i += 8 * 256) {
+        float g[8];
+        asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0,%1,%2,%3}, [%4];"
+                     : "=f"(g[0]), "=f"(g[1]), "=f"(g[2]), "=f"(g[3]) : "l"(g_mc + i) : "memory");
+        asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0,%1,%2,%3}, [%4];"
+                     : "=f"(g[4]), "=f"(g[5]), "=f"(g[6]), "=f"(g[7]) : "l"(g_mc + i + 4) : "memory");
+        const float4 p0 = *reinterpret_cast<const float4*>(p + i), p1 = *reinterpret_cast<const float4*>(p + i + 4);
+        const float4 b0 = *reinterpret_cast<const float4*>(mb + i), b1 = *reinterpret_cast<const float4*>(mb + i + 4);
+        const float pv[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
+        const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+        float np[8], nb[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            nb[k] = mom * bv[k] + (g[k] * gs + wd * pv[k]);
+            np[k] = pv[k] - lr * nb[k];
+        }
+        *reinterpret_cast<float4*>(mb + i) = make_float4(nb[0], nb[1], nb[2], nb[3]);
+        *reinterpret_cast<float4*>(mb + i + 4) = make_float4(nb[4], nb[5], nb[6], nb[7]);
+        *reinterpret_cast<float4*>(p + i) = make_float4(np[0], np[1], np[2], np[3]);
+        *reinterpret_cast<float4*>(p + i + 4) = make_float4(np[4], np[5], np[6], np[7]);
+        uint32_t u[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const __nv_bfloat162 q = __floats2bfloat162_rn(np[2 * k], np[2 * k + 1]);
+            u[k] = *reinterpret_cast<const uint32_t*>(&q);
+        }
+        asm volatile("multimem.st.relaxed.sys.global.v4.bf16x2 [%0], {%1,%2,%3,%4};" ::"l"(ob_mc + i), "r"(u[0]), "r"(u[1]),
+                     "r"(u[2]), "r"(u[3]) : "memory");
+    }
+    __threadfence_system();   // this thread's multicast stores are performed system-wide before the kernel retires
+}
+
 }  // namespace soswsod
 
 using namespace soswsod;
+
+extern "C" int soswsod_sgd_nvls(const soswsod_sgd_nvls_tensor* tensors, int count, float momentum, float grad_scale,
+                                soswsod_stream_t stream) {
+    SOSWSOD_CHECK_ARG(tensors && count > 0 && count <= SOSWSOD_SGD_NVLS_MAX_TENSORS, "sgd_nvls: 1..%d tensors per call",
+                      SOSWSOD_SGD_NVLS_MAX_TENSORS);
+    SgdNvlsBatch b;
+    b.count = count;
+    b.momentum = momentum;
+    b.gscale = grad_scale;
+    long long blocks = 0;
+    for (int i = 0; i < count; ++i) {
+        const soswsod_sgd_nvls_tensor& t = tensors[i];
+        SOSWSOD_CHECK_ARG(t.param && t.grad_mc && t.momentum_buf && t.out_bf16_mc && t.n > 0, "sgd_nvls: tensor %d: null pointer or empty", i);
+        SOSWSOD_CHECK_ARG(t.n % 8 == 0, "sgd_nvls: tensor %d: %lld elements, need a multiple of 8", i, t.n);
+        SOSWSOD_CHECK_ARG(((reinterpret_cast<uintptr_t>(t.param) | reinterpret_cast<uintptr_t>(t.grad_mc) |
+                            reinterpret_cast<uintptr_t>(t.momentum_buf) | reinterpret_cast<uintptr_t>(t.out_bf16_mc)) & 15) == 0,
+                          "sgd_nvls: tensor %d: pointers must be 16-byte aligned", i);
+        b.t[i] = t;
+        b.block_start[i] = (int)blocks;
+        blocks += (t.n + kSgdBlockElems - 1) / kSgdBlockElems;
+        SOSWSOD_CHECK_ARG(blocks < (1LL << 30), "sgd_nvls: too many elements for one launch");
+    }
+    b.block_start[count] = (int)blocks;
+    sgd_nvls_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(b);
+    SOSWSOD_CHECK_LAUNCH();
+    return SOSWSOD_OK;
+}
 
 extern "C" int soswsod_sgd_multi(const soswsod_sgd_tensor* tensors, int count, float momentum, float grad_scale,
                                  soswsod_stream_t stream) {

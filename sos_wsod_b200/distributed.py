@@ -2,7 +2,7 @@
 the reference wraps the model in DistributedDataParallel, uwsod/projects/WSL/tools/train_net_multi.py:75-78, which
 all-reduces 483.8 MB of fp32 gradients per rank and step and then runs the full optimizer on every rank).
 
-Two modes behind one object, both giving every rank the SAME fp32 result as DDP's average:
+Three modes behind one object, all giving every rank the SAME fp32 result as DDP's average:
 
   "allreduce"  what DDP does: an averaging all-reduce per gradient, started from the engine's gradient hook as soon as
                the producing kernel is queued.
@@ -15,6 +15,13 @@ Two modes behind one object, both giving every rank the SAME fp32 result as DDP'
                rank does not own are refreshed on demand (`sync_master()`: state_dict / checkpoint time); the forward
                and backward only ever read the bf16 operands.  Small tensors (biases, the fused head block) are
                all-reduced.
+
+  "nvls"       the sharded scheme with NO collective library on the big tensors: the weight gradients of fc1 / fc2 and
+               their bf16 operands live in symmetric memory mapped for NVSwitch multicast
+               (torch.distributed._symmetric_memory); ONE kernel per rank (soswsod_sgd_nvls) reads the sum over the
+               ranks of its rows' gradient through the switch (multimem.ld_reduce), applies the update and stores the
+               refreshed operand rows to every rank (multimem.st).  Two cross-rank barriers bracket it.  The backward
+               runs without any NCCL kernel next to it (no row panels needed); the small tensors are all-reduced.
 
 Every collective is issued with async_op=True from the stream that produced its input; `Work.wait()` orders the
 consumer's stream behind it -- no host synchronisation anywhere.  The consumer is the exchange's UPDATE STREAM
@@ -38,7 +45,7 @@ class GradientExchange:
         """master: HeadOperands.master (key -> fp32 parameter).  mode: "sharded" | "allreduce"."""
         if not dist.is_initialized():
             raise RuntimeError("GradientExchange needs an initialised torch.distributed process group")
-        assert mode in ("sharded", "allreduce")
+        assert mode in ("sharded", "allreduce", "nvls")
         self.group = group
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
@@ -47,7 +54,10 @@ class GradientExchange:
         self.native = self.backend == "nccl"
         self.master = master
         self.sharded = set()
-        if mode == "sharded" and self.world > 1:
+        self.symm = None                 # nvls: handle of the symmetric arena
+        self.symm_tensors: Dict[str, torch.Tensor] = {}     # nvls: "g:<key>" fp32 gradient, "w:<key>" bf16 operand
+        self._symm_offsets: Dict[str, int] = {}
+        if mode in ("sharded", "nvls") and self.world > 1:
             for k in self.SHARDED_KEYS:
                 t = master[k]
                 if t.numel() >= min_shard_elems and t.size(0) % self.world == 0:
@@ -73,9 +83,52 @@ class GradientExchange:
         self._rs.clear()
         self.bytes_last_step = {"reduce_scatter": 0, "all_reduce": 0, "all_gather": 0}
 
+    # ------------------------------------------------------------------ nvls: symmetric multicast memory
+    def setup_nvls(self) -> None:
+        """Allocates ONE symmetric arena holding, for every sharded matrix, its fp32 gradient and its bf16 GEMM operand,
+        and maps it for multicast.  Raises RuntimeError when the platform has no NVLS multicast."""
+        import torch.distributed._symmetric_memory as symm_mem
+
+        dev = next(iter(self.master.values())).device
+        off, plan = 0, []
+        for key in sorted(self.sharded):
+            shape = tuple(self.master[key].shape)
+            n = self.master[key].numel()
+            for tag, dt, nbytes in (("g", torch.float32, 4 * n), ("w", torch.bfloat16, 2 * n)):
+                plan.append((f"{tag}:{key}", dt, shape, off, nbytes))
+                off += (nbytes + 255) // 256 * 256
+        arena = symm_mem.empty(off, dtype=torch.uint8, device=dev)
+        group = self.group if self.group is not None else dist.group.WORLD
+        self.symm = symm_mem.rendezvous(arena, group=group)
+        if not getattr(self.symm, "has_multicast_support", False) or int(self.symm.multicast_ptr) == 0:
+            raise RuntimeError("GradientExchange(mode='nvls'): the symmetric-memory rendezvous gave no multicast address "
+                               "(no NVSwitch multicast on this platform); use mode='sharded'")
+        self._arena = arena
+        for name, dt, shape, o, nbytes in plan:
+            self.symm_tensors[name] = arena[o:o + nbytes].view(dt).view(shape)
+            self._symm_offsets[name] = o
+        self._layout = {key: [(0, self.master[key].size(0))] for key in self.sharded}
+
+    def multicast_address(self, name: str, row0: int = 0) -> int:
+        """Multicast virtual address of row `row0` of symmetric tensor `name` ("g:fc1_w", "w:fc2_w", ...)."""
+        t = self.symm_tensors[name]
+        return int(self.symm.multicast_ptr) + self._symm_offsets[name] + row0 * t.stride(0) * t.element_size()
+
+    def barrier(self) -> None:
+        """Cross-rank barrier on the current stream (signal pads of the symmetric arena; no host synchronisation)."""
+        self.symm.barrier(channel=0)
+
     def hook(self, key: str, grad: torch.Tensor, row0: int) -> None:
         """The engine's grad_hook: starts the collective of one gradient (or one row panel of fc1.weight)."""
         if self.world == 1:
+            return
+        if self.mode == "nvls" and key in self.sharded:
+            # nothing to start: the engine wrote the gradient straight into the symmetric buffer; the fused update pulls
+            # the ranks' sum through the switch
+            if grad.data_ptr() != self.symm_tensors[f"g:{key}"].data_ptr() + row0 * grad.stride(0) * 4:
+                raise RuntimeError(f"GradientExchange(nvls): the gradient of {key} was not produced in the symmetric buffer")
+            self.bytes_last_step["nvls_ld_reduce"] = self.bytes_last_step.get("nvls_ld_reduce", 0) + grad.numel() * 4 // self.world
+            self.bytes_last_step["nvls_multicast_store"] = self.bytes_last_step.get("nvls_multicast_store", 0) + grad.numel() * 2 // self.world
             return
         # Work on an independent tensor over the same storage: a reference to `grad` itself (or to a view of it, which
         # keeps its base alive) held by this object or by the process group would make autograd's AccumulateGrad CLONE the
@@ -115,11 +168,18 @@ class GradientExchange:
         for _, _, _, w in self._rs:
             w.wait()
 
+    def owned_rows_nvls(self, key: str) -> Tuple[int, int]:
+        rows = self.master[key].size(0)
+        per = rows // self.world
+        return self.rank * per, (self.rank + 1) * per
+
     def owned_rows(self, key: str) -> List[Tuple[int, int]]:
         """Row ranges [lo, hi) of parameter `key` this rank updates (after wait_gradients): one per exchanged panel for
         a sharded tensor -- the averaged gradient of exactly those rows sits in the gradient tensor -- else all rows."""
         if key not in self.sharded:
             return [(0, self.master[key].size(0))]
+        if self.mode == "nvls":
+            return [self.owned_rows_nvls(key)]
         out = []
         for k, panel, row0, _ in self._rs:
             if k == key:

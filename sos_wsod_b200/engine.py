@@ -110,6 +110,16 @@ class HeadOperands:
         """Forces the next refresh(force=False) to re-cast every operand."""
         self._versions = None
 
+    def adopt_operand_storage(self, w6: Optional[torch.Tensor] = None, w7: Optional[torch.Tensor] = None) -> None:
+        """Moves the fc6 / fc7 bf16 operands into caller-owned memory of the same shape (symmetric multicast memory of
+        the nvls gradient exchange), keeping their current values."""
+        for name, t in (("w6", w6), ("w7", w7)):
+            if t is not None:
+                cur = getattr(self, name)
+                assert t.shape == cur.shape and t.dtype == cur.dtype and t.device == cur.device
+                t.copy_(cur)
+                setattr(self, name, t)
+
     def mark_fresh(self) -> None:
         """Declares the operands up to date with the master parameters as they are now -- called by an optimizer that
         wrote the bf16 copies itself in its update pass (solver.B200SGD)."""
@@ -186,6 +196,7 @@ class OICRPlusHeadEngine:
         # step (the caller consumes them before the next step); never with autograd, which adopts the buffers as .grad
         self.persistent_grads = False
         self._grad_bufs: Dict[str, torch.Tensor] = {}
+        self.external_grad_bufs: Dict[str, torch.Tensor] = {}     # "fc1_w" / "fc2_w" / "head_w" -> caller-owned fp32 buffers
         self._side_stream = None
 
     def _operands_ready(self):
@@ -290,6 +301,13 @@ class OICRPlusHeadEngine:
         side = self._side() if (grad_hook is None and self.bias_on_side_stream) else None
 
         def grad_buf(name, shape):
+            ext = self.external_grad_bufs.get(name)
+            if ext is not None:          # e.g. symmetric multicast memory of the nvls gradient exchange
+                assert tuple(ext.shape) == tuple(shape) and ext.dtype == torch.float32
+                # a fresh tensor object over the same memory: autograd adopts it as `.grad` (a second reference to one
+                # tensor object would make it clone 478 MB per step)
+                return torch.empty(0, dtype=ext.dtype, device=ext.device).set_(ext.untyped_storage(), ext.storage_offset(),
+                                                                              ext.shape, ext.stride())
             if not self.persistent_grads:
                 return None
             t = self._grad_bufs.get(name)

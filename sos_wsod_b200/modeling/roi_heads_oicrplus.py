@@ -282,6 +282,14 @@ class OICRPlusHeads(nn.Module):
         eng = self.engine()
         self.exchange = GradientExchange(eng.op.master, group=group, mode=mode)
         self.grad_hook = self.exchange.hook if self.exchange.world > 1 else None
+        if mode == "nvls" and self.exchange.world > 1:
+            ex = self.exchange
+            ex.setup_nvls()
+            # the engine writes the big weight gradients straight into the symmetric buffers (one launch each: no row
+            # panels, nothing to overlap) and computes with the symmetric operands the fused update broadcasts into
+            eng.external_grad_bufs.update({k: ex.symm_tensors[f"g:{k}"] for k in ex.sharded})
+            eng.op.adopt_operand_storage(w6=ex.symm_tensors.get("w:fc1_w"), w7=ex.symm_tensors.get("w:fc2_w"))
+            eng.fc1_wgrad_panels = 1
         self.engine()
         return self.exchange
 

@@ -307,6 +307,31 @@ def sgd_multi(items, momentum: float, grad_scale: float = 1.0) -> int:
     return n_launch
 
 
+def sgd_nvls(items, momentum: float, grad_scale: float) -> int:
+    """The fused NVLS update (soswsod_sgd_nvls).  items: iterable of (param_rows, grad_mc_address, momentum_rows,
+    operand_mc_address, lr, weight_decay) -- param / momentum rows are contiguous fp32 CUDA tensors (the rows this rank
+    owns), the two addresses are multicast virtual addresses (int) of the same rows in the symmetric gradient / bf16
+    operand buffers."""
+    import ctypes
+
+    items = list(items)
+    if not items:
+        return 0
+    if len(items) > _lib.SGD_NVLS_MAX_TENSORS:
+        raise RuntimeError(f"sgd_nvls: at most {_lib.SGD_NVLS_MAX_TENSORS} tensors per call")
+    arr = (_lib.SgdNvlsTensor * len(items))()
+    for d, (p, g_mc, buf, ob_mc, lr, wd) in zip(arr, items):
+        _need_cuda(p, buf)
+        if not (p.is_contiguous() and buf.is_contiguous() and p.dtype == buf.dtype == torch.float32 and p.numel() == buf.numel()):
+            raise RuntimeError("sgd_nvls: param / momentum rows must be contiguous fp32 tensors of one size")
+        d.param, d.grad_mc, d.momentum_buf, d.out_bf16_mc = p.data_ptr(), int(g_mc), buf.data_ptr(), int(ob_mc)
+        d.n, d.lr, d.weight_decay = p.numel(), float(lr), float(wd)
+    check(_lib.load().soswsod_sgd_nvls(ctypes.cast(arr, ctypes.c_void_p), len(items), float(momentum), float(grad_scale),
+                                       _stream()), "sgd_nvls")
+    _count(1)
+    return 1
+
+
 # ------------------------------------------------------------------------------------------------
 # (3) WSDDN
 # ------------------------------------------------------------------------------------------------

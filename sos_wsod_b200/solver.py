@@ -122,11 +122,14 @@ class B200SGD(torch.optim.Optimizer):
             ready.record()                       # every gradient kernel of the step is queued behind this point
             update_stream.wait_event(ready)
         ctx = torch.cuda.stream(update_stream) if update_stream is not None else contextlib.nullcontext()
+        nvls_items, nvls_params = [], set()
         with ctx:
             for h, ex in exchanges:
                 ex.wait_gradients()
                 for key in sorted(ex.sharded):
                     shard_rows[id(ex.master[key])] = ex.owned_rows(key)
+                    if ex.mode == "nvls":
+                        nvls_params.add(id(ex.master[key]))
             by_momentum, touched = {}, []          # the reference makes one group per parameter: batch across groups
             for group in self.param_groups:
                 for p in group["params"]:
@@ -142,21 +145,39 @@ class B200SGD(torch.optim.Optimizer):
                         raise RuntimeError("B200SGD needs contiguous parameters")
                     if id(p) in key_of:
                         key_of[id(p)][0].check_gradient_buffer(key_of[id(p)][1], p.grad)
-                    if update_stream is not None:
+                    if update_stream is not None and id(p) not in nvls_params:
                         grad.record_stream(update_stream)     # `.grad` may be dropped by the host before the update ran
                     ob, of = sinks.get(id(p), (None, None))
                     items = by_momentum.setdefault(float(group["momentum"]), [])
                     pd, buf = p.detach(), st["momentum_buffer"]
+                    if id(p) in nvls_params:
+                        # fused reduce-scatter + update + all-gather over NVSwitch multicast: this rank's rows only
+                        ex, key = key_of[id(p)]
+                        lo, hi = ex.owned_rows_nvls(key)
+                        nvls_items.append((float(group["momentum"]), ex, (pd[lo:hi], ex.multicast_address(f"g:{key}", lo), buf[lo:hi],
+                                                                          ex.multicast_address(f"w:{key}", lo), group["lr"], group["weight_decay"])))
+                        touched.append(p)
+                        continue
                     for lo, hi in shard_rows.get(id(p), [(0, p.size(0) if p.dim() else 1)]):
                         whole = (lo == 0 and hi == (p.size(0) if p.dim() else 1))
                         sl = (lambda t: t) if whole else (lambda t, lo=lo, hi=hi: None if t is None else t[lo:hi])
                         items.append((sl(pd), sl(grad), sl(buf), group["lr"], group["weight_decay"], sl(ob), sl(of)))
                     touched.append(p)
+            if nvls_items:
+                ex = nvls_items[0][1]
+                ex.barrier()             # every rank's weight gradients are complete in the symmetric buffers
+                for momentum in sorted({m for m, _, _ in nvls_items}):
+                    self.launches_last_step += ops.sgd_nvls([it for m, _, it in nvls_items if m == momentum], momentum, 1.0 / ex.world)
             for momentum, items in by_momentum.items():
                 self.launches_last_step += ops.sgd_multi(items, momentum)
+            if nvls_items:
+                nvls_items[0][1].barrier()   # every rank's operand rows have landed everywhere; the gradient buffers are free
             for h, ex in exchanges:
-                op = h.engine().op
-                ex.gather_operands({"fc1_w": op.w6, "fc2_w": op.w7})
+                if ex.mode == "nvls":
+                    ex.master_stale = True
+                else:
+                    op = h.engine().op
+                    ex.gather_operands({"fc1_w": op.w6, "fc2_w": op.w7})
                 ex.mark_update_done()
         for p in touched:
             # the kernel wrote through raw pointers: bump the version counters like an in-place op would
