@@ -445,8 +445,8 @@ def run_b200_arm(args):
     blocks_per_step = [b / K_steps for b in blocks_ms]
 
     # ---- untimed pass with per-kernel CUDA events: roofline of the dominant kernel + the ROI kernels + the SGD pass ----
-    gemm_events, roi_events, sgd_events = [], {"fwd": [], "bwd": []}, []
-    orig_gemm, orig_fwd, orig_bwd, orig_sgd = ops.gemm_bf16, ops.roi_pool_forward, ops.roi_pool_backward, ops.sgd_multi
+    gemm_events, roi_events, sgd_events, nvls_events = [], {"fwd": [], "bwd": []}, [], []
+    orig_gemm, orig_fwd, orig_bwd, orig_sgd, orig_nvls = ops.gemm_bf16, ops.roi_pool_forward, ops.roi_pool_backward, ops.sgd_multi, ops.sgd_nvls
 
     def timed_gemm(a, b, **kw):
         # allocate the output BEFORE the first event: an allocator call between the events (cudaMalloc of a 411 MB block
@@ -479,12 +479,14 @@ def run_b200_arm(args):
     ops.roi_pool_forward = timed(roi_events["fwd"], orig_fwd)
     ops.roi_pool_backward = timed(roi_events["bwd"], orig_bwd)
     ops.sgd_multi = timed(sgd_events, orig_sgd)
+    ops.sgd_nvls = timed(nvls_events, orig_nvls)
     ev_steps = max(5, min(20, K_steps))
     for i in range(3):          # the event pass's own allocation pattern, untimed
         device_step(1900 + i)
     sync_all()
     gemm_events.clear()
     sgd_events.clear()
+    nvls_events.clear()
     for v in roi_events.values():
         v.clear()
     w0 = time.perf_counter()
@@ -498,7 +500,7 @@ def run_b200_arm(args):
     sync_all()
     sampler.window(w0, time.perf_counter())
     ev_pass_ms_per_step = ea.elapsed_time(eb) / ev_steps
-    ops.gemm_bf16, ops.roi_pool_forward, ops.roi_pool_backward, ops.sgd_multi = orig_gemm, orig_fwd, orig_bwd, orig_sgd
+    ops.gemm_bf16, ops.roi_pool_forward, ops.roi_pool_backward, ops.sgd_multi, ops.sgd_nvls = orig_gemm, orig_fwd, orig_bwd, orig_sgd, orig_nvls
 
     tot_flops = sum(e[2] for e in gemm_events)
     tot_ms = sum(e[0].elapsed_time(e[1]) for e in gemm_events)
@@ -569,6 +571,14 @@ def run_b200_arm(args):
                             "hbm_gbs": sgd_bytes / (sgd_ms * 1e-3) / 1e9 if sgd_ms > 0 else 0.0,
                             "frac_of_hbm_peak": (sgd_bytes / (sgd_ms * 1e-3) / 1e9) / peaks["hbm_gbs"] if sgd_ms > 0 else 0.0,
                             "bound": "hbm", "params": n_params, "rows_updated_fraction": shard}
+    if nvls_events:
+        nv_ms = sum(e0.elapsed_time(e1) for e0, e1 in nvls_events) / ev_steps
+        big = sum(master[k].numel() for k in ex.sharded)
+        roofline["nvls_update"] = {"kernel": "sgd_nvls_kernel (multimem.ld_reduce + SGD + multimem.st)", "ms_per_step": nv_ms,
+                                   "launches_per_step": len(nvls_events) // ev_steps,
+                                   "nvlink_bytes_out_per_rank": big * 4 * (world - 1) // world + big * 2 // world,
+                                   "local_hbm_bytes": big // world * (4 + 8 + 8 + 2),
+                                   "note": "timed on the update stream next to the compute stream's kernels"}
 
     # ---- N > 1: the exchange gives every rank the mean of the ranks' gradients (checked outside any timed region) ----
     exchange_check = None

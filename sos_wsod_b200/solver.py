@@ -9,6 +9,7 @@ the head's bf16 GEMM operands in the same pass.  Gradient clipping (SOLVER.CLIP_
 from __future__ import annotations
 
 import contextlib
+import os
 from typing import Any, Dict, List, Set
 
 import torch
@@ -117,6 +118,8 @@ class B200SGD(torch.optim.Optimizer):
                 for key, prm in ex.master.items():
                     key_of[id(prm)] = (ex, key)
         update_stream = exchanges[0][1].update_stream() if exchanges else None
+        if update_stream is not None and os.environ.get("SOSWSOD_UPDATE_ON_MAIN"):      # diagnosis: serialise the update
+            update_stream = torch.cuda.current_stream()
         if update_stream is not None:
             ready = torch.cuda.Event()
             ready.record()                       # every gradient kernel of the step is queued behind this point
