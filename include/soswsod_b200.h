@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define SOSWSOD_ABI_VERSION 9
+#define SOSWSOD_ABI_VERSION 10
 
 #define SOSWSOD_OK 0
 #define SOSWSOD_ERR_INVALID (-1)     /* bad shape / null pointer / misalignment */
@@ -329,7 +329,7 @@ int soswsod_sgd_multi(const soswsod_sgd_tensor* tensors, int count, float moment
  *   SGD + momentum + weight decay on the local fp32 rows, and the refreshed bf16 operand rows stored with multimem.st
  *   to the multicast address out_bf16_mc (they land in every rank's operand matrix).
  * param / momentum_buf: local device pointers; grad_mc / out_bf16_mc: multicast virtual addresses of symmetric buffers
- * (cuMulticast* / torch symmetric memory), all pre-offset to the owned rows; n % 8 == 0, 16-byte aligned.  The caller
+ * (cuMulticast* / torch symmetric memory), all pre-offset to the owned rows; n % 4 == 0, fp32 pointers 16-byte aligned.  The caller
  * provides the cross-rank barriers: every rank's gradient complete before the launch; all launches complete before
  * any rank reads the operands or overwrites the gradients.  `tensors` is a HOST array. */
 #define SOSWSOD_SGD_NVLS_MAX_TENSORS 8
@@ -343,7 +343,7 @@ typedef struct soswsod_sgd_nvls_tensor {
     float weight_decay;
 } soswsod_sgd_nvls_tensor;
 int soswsod_sgd_nvls(const soswsod_sgd_nvls_tensor* tensors, int count, float momentum, float grad_scale,
-                     soswsod_stream_t stream);
+                     int max_ctas /* persistent grid size; <= 0: 2 per SM */, soswsod_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * (6) PGF, the consumer of the detection-results json.  Replaces the per-image

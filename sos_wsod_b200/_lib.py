@@ -10,7 +10,7 @@ from ctypes import c_char_p, c_double, c_float, c_int, c_longlong, c_size_t, c_u
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libsoswsod_b200.so")
-ABI_VERSION = 9
+ABI_VERSION = 10
 
 DTYPE_F32, DTYPE_BF16 = 0, 1
 ARGMAX_I32, ARGMAX_U16 = 0, 1
@@ -57,7 +57,7 @@ SIGNATURES = {
     "soswsod_pgf": (c_int, [_P, _P, _P, _P, c_int, c_double, c_double, c_int, c_ulonglong, c_ulonglong, _P, _P]),
     "soswsod_sgd_step": (c_int, [_P, _P, _P, c_longlong, c_float, c_float, c_float, c_float, _P, _P]),
     "soswsod_sgd_multi": (c_int, [_P, c_int, c_float, c_float, _P]),
-    "soswsod_sgd_nvls": (c_int, [_P, c_int, c_float, c_float, _P]),
+    "soswsod_sgd_nvls": (c_int, [_P, c_int, c_float, c_float, c_int, _P]),
 }
 
 

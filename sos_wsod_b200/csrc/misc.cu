@@ -245,53 +245,71 @@ sgd_multi_kernel(const __grid_constant__ SgdBatch b) {
 //     all-gather).
 // grad_mc / out_bf16_mc are multicast addresses of symmetric buffers (same offset on every rank); the caller brackets
 // the launch with cross-rank barriers (all gradients written before, all operand rows landed after).
+static int device_num_sms_misc() {
+    static int sms = 0;
+    if (sms == 0) {
+        int dev = 0, v = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0) sms = v;
+        else sms = 148;
+    }
+    return sms;
+}
+
+constexpr int kNvlsThreads = 512;
+constexpr int kNvlsPerThread = 16;                              // elements per thread and iteration: 4 x 16-byte ld_reduce in flight
+constexpr int kNvlsChunk = kNvlsThreads * kNvlsPerThread;       // 8192 elements
+
 struct SgdNvlsBatch {
     soswsod_sgd_nvls_tensor t[SOSWSOD_SGD_NVLS_MAX_TENSORS];
-    int block_start[SOSWSOD_SGD_NVLS_MAX_TENSORS + 1];
+    long long chunk_start[SOSWSOD_SGD_NVLS_MAX_TENSORS + 1];
     int count;
     float momentum, gscale;
 };
 
-__global__ void __launch_bounds__(256)
+// Persistent grid: the switch serves a bounded number of outstanding multimem requests well (NCCL / torch drive NVLS with
+// a few dozen CTAs); every CTA walks the chunk list with stride gridDim.x, every thread keeps four 16-byte reductions in
+// flight per iteration.
+__global__ void __launch_bounds__(kNvlsThreads)
 sgd_nvls_kernel(const __grid_constant__ SgdNvlsBatch b) {
-    int ti = 0;
-    while (ti + 1 < b.count && (int)blockIdx.x >= b.block_start[ti + 1]) ++ti;
-    const soswsod_sgd_nvls_tensor& t = b.t[ti];
-    const long long e0 = (long long)((int)blockIdx.x - b.block_start[ti]) * kSgdBlockElems;
-    const long long e1 = e0 + kSgdBlockElems < t.n ? e0 + kSgdBlockElems : t.n;
-    float* __restrict__ p = t.param;
-    float* __restrict__ mb = t.momentum_buf;
-    const float* g_mc = t.grad_mc;
-    __nv_bfloat16* ob_mc = reinterpret_cast<__nv_bfloat16*>(t.out_bf16_mc);
-    const float lr = t.lr, wd = t.weight_decay, mom = b.momentum, gs = b.gscale;
-    for (long long i = e0 + 8LL * threadIdx.x; i + 8 <= e1; i += 8 * 256) {
-        float g[8];
-        asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0,%1,%2,%3}, [%4];"
-                     : "=f"(g[0]), "=f"(g[1]), "=f"(g[2]), "=f"(g[3]) : "l"(g_mc + i) : "memory");
-        asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0,%1,%2,%3}, [%4];"
-                     : "=f"(g[4]), "=f"(g[5]), "=f"(g[6]), "=f"(g[7]) : "l"(g_mc + i + 4) : "memory");
-        const float4 p0 = *reinterpret_cast<const float4*>(p + i), p1 = *reinterpret_cast<const float4*>(p + i + 4);
-        const float4 b0 = *reinterpret_cast<const float4*>(mb + i), b1 = *reinterpret_cast<const float4*>(mb + i + 4);
-        const float pv[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
-        const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-        float np[8], nb[8];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            nb[k] = mom * bv[k] + (g[k] * gs + wd * pv[k]);
-            np[k] = pv[k] - lr * nb[k];
-        }
-        *reinterpret_cast<float4*>(mb + i) = make_float4(nb[0], nb[1], nb[2], nb[3]);
-        *reinterpret_cast<float4*>(mb + i + 4) = make_float4(nb[4], nb[5], nb[6], nb[7]);
-        *reinterpret_cast<float4*>(p + i) = make_float4(np[0], np[1], np[2], np[3]);
-        *reinterpret_cast<float4*>(p + i + 4) = make_float4(np[4], np[5], np[6], np[7]);
-        uint32_t u[4];
+    const long long total = b.chunk_start[b.count];
+    for (long long c = blockIdx.x; c < total; c += gridDim.x) {
+        int ti = 0;
+        while (ti + 1 < b.count && c >= b.chunk_start[ti + 1]) ++ti;
+        const soswsod_sgd_nvls_tensor& t = b.t[ti];
+        const long long i = (c - b.chunk_start[ti]) * kNvlsChunk + (long long)threadIdx.x * 4;
+        float* __restrict__ p = t.param;
+        float* __restrict__ mb = t.momentum_buf;
+        const float* g_mc = t.grad_mc;
+        __nv_bfloat16* ob_mc = reinterpret_cast<__nv_bfloat16*>(t.out_bf16_mc);
+        const float lr = t.lr, wd = t.weight_decay, mom = b.momentum, gs = b.gscale;
+        // four groups of 4 consecutive elements, kNvlsThreads * 4 apart: a warp's 32 lanes read 512 contiguous bytes
+        float4 g[4];
+        bool live[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            const __nv_bfloat162 q = __floats2bfloat162_rn(np[2 * k], np[2 * k + 1]);
-            u[k] = *reinterpret_cast<const uint32_t*>(&q);
+            const long long e = i + (long long)k * kNvlsThreads * 4;
+            live[k] = e + 4 <= t.n;
+            if (live[k])
+                asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0,%1,%2,%3}, [%4];"
+                             : "=f"(g[k].x), "=f"(g[k].y), "=f"(g[k].z), "=f"(g[k].w) : "l"(g_mc + e) : "memory");
         }
-        asm volatile("multimem.st.relaxed.sys.global.v4.bf16x2 [%0], {%1,%2,%3,%4};" ::"l"(ob_mc + i), "r"(u[0]), "r"(u[1]),
-                     "r"(u[2]), "r"(u[3]) : "memory");
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (!live[k]) continue;
+            const long long e = i + (long long)k * kNvlsThreads * 4;
+            const float4 pv = *reinterpret_cast<const float4*>(p + e);
+            const float4 bv = *reinterpret_cast<const float4*>(mb + e);
+            float4 nb, np;
+            nb.x = mom * bv.x + (g[k].x * gs + wd * pv.x); np.x = pv.x - lr * nb.x;
+            nb.y = mom * bv.y + (g[k].y * gs + wd * pv.y); np.y = pv.y - lr * nb.y;
+            nb.z = mom * bv.z + (g[k].z * gs + wd * pv.z); np.z = pv.z - lr * nb.z;
+            nb.w = mom * bv.w + (g[k].w * gs + wd * pv.w); np.w = pv.w - lr * nb.w;
+            *reinterpret_cast<float4*>(mb + e) = nb;
+            *reinterpret_cast<float4*>(p + e) = np;
+            const __nv_bfloat162 q0 = __floats2bfloat162_rn(np.x, np.y), q1 = __floats2bfloat162_rn(np.z, np.w);
+            asm volatile("multimem.st.relaxed.sys.global.v2.bf16x2 [%0], {%1,%2};" ::"l"(ob_mc + e),
+                         "r"(*reinterpret_cast<const uint32_t*>(&q0)), "r"(*reinterpret_cast<const uint32_t*>(&q1)) : "memory");
+        }
     }
     __threadfence_system();   // this thread's multicast stores are performed system-wide before the kernel retires
 }
@@ -301,28 +319,30 @@ sgd_nvls_kernel(const __grid_constant__ SgdNvlsBatch b) {
 using namespace soswsod;
 
 extern "C" int soswsod_sgd_nvls(const soswsod_sgd_nvls_tensor* tensors, int count, float momentum, float grad_scale,
-                                soswsod_stream_t stream) {
+                                int max_ctas, soswsod_stream_t stream) {
     SOSWSOD_CHECK_ARG(tensors && count > 0 && count <= SOSWSOD_SGD_NVLS_MAX_TENSORS, "sgd_nvls: 1..%d tensors per call",
                       SOSWSOD_SGD_NVLS_MAX_TENSORS);
     SgdNvlsBatch b;
     b.count = count;
     b.momentum = momentum;
     b.gscale = grad_scale;
-    long long blocks = 0;
+    long long chunks = 0;
     for (int i = 0; i < count; ++i) {
         const soswsod_sgd_nvls_tensor& t = tensors[i];
         SOSWSOD_CHECK_ARG(t.param && t.grad_mc && t.momentum_buf && t.out_bf16_mc && t.n > 0, "sgd_nvls: tensor %d: null pointer or empty", i);
-        SOSWSOD_CHECK_ARG(t.n % 8 == 0, "sgd_nvls: tensor %d: %lld elements, need a multiple of 8", i, t.n);
+        SOSWSOD_CHECK_ARG(t.n % 4 == 0, "sgd_nvls: tensor %d: %lld elements, need a multiple of 4", i, t.n);
         SOSWSOD_CHECK_ARG(((reinterpret_cast<uintptr_t>(t.param) | reinterpret_cast<uintptr_t>(t.grad_mc) |
-                            reinterpret_cast<uintptr_t>(t.momentum_buf) | reinterpret_cast<uintptr_t>(t.out_bf16_mc)) & 15) == 0,
-                          "sgd_nvls: tensor %d: pointers must be 16-byte aligned", i);
+                            reinterpret_cast<uintptr_t>(t.momentum_buf)) & 15) == 0 &&
+                              (reinterpret_cast<uintptr_t>(t.out_bf16_mc) & 7) == 0,
+                          "sgd_nvls: tensor %d: fp32 pointers must be 16-byte, the bf16 operand 8-byte aligned", i);
         b.t[i] = t;
-        b.block_start[i] = (int)blocks;
-        blocks += (t.n + kSgdBlockElems - 1) / kSgdBlockElems;
-        SOSWSOD_CHECK_ARG(blocks < (1LL << 30), "sgd_nvls: too many elements for one launch");
+        b.chunk_start[i] = chunks;
+        chunks += (t.n + kNvlsChunk - 1) / kNvlsChunk;
     }
-    b.block_start[count] = (int)blocks;
-    sgd_nvls_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(b);
+    b.chunk_start[count] = chunks;
+    if (max_ctas <= 0) max_ctas = 2 * device_num_sms_misc();
+    const long long grid = chunks < max_ctas ? chunks : max_ctas;
+    sgd_nvls_kernel<<<(unsigned)grid, kNvlsThreads, 0, (cudaStream_t)stream>>>(b);
     SOSWSOD_CHECK_LAUNCH();
     return SOSWSOD_OK;
 }

@@ -307,6 +307,9 @@ def sgd_multi(items, momentum: float, grad_scale: float = 1.0) -> int:
     return n_launch
 
 
+NVLS_MAX_CTAS = 0      # persistent grid of the fused NVLS update; 0 = the library default (2 per SM)
+
+
 def sgd_nvls(items, momentum: float, grad_scale: float) -> int:
     """The fused NVLS update (soswsod_sgd_nvls).  items: iterable of (param_rows, grad_mc_address, momentum_rows,
     operand_mc_address, lr, weight_decay) -- param / momentum rows are contiguous fp32 CUDA tensors (the rows this rank
@@ -327,7 +330,7 @@ def sgd_nvls(items, momentum: float, grad_scale: float) -> int:
         d.param, d.grad_mc, d.momentum_buf, d.out_bf16_mc = p.data_ptr(), int(g_mc), buf.data_ptr(), int(ob_mc)
         d.n, d.lr, d.weight_decay = p.numel(), float(lr), float(wd)
     check(_lib.load().soswsod_sgd_nvls(ctypes.cast(arr, ctypes.c_void_p), len(items), float(momentum), float(grad_scale),
-                                       _stream()), "sgd_nvls")
+                                       int(NVLS_MAX_CTAS), _stream()), "sgd_nvls")
     _count(1)
     return 1
 
