@@ -55,7 +55,9 @@ class GradientExchange:
         self.master = master
         self.sharded = set()
         self.symm = None                 # nvls: handle of the symmetric arena
-        self.symm_tensors: Dict[str, torch.Tensor] = {}     # nvls: "g:<key>" fp32 gradient, "w:<key>" bf16 operand
+        self.symm_tensors: Dict[str, torch.Tensor] = {}     # nvls: "g:<key>" fp32 gradient, "w0:<key>" / "w1:<key>" bf16 operands
+        self.operand_slot = 0            # nvls: which operand copy the engine computes with in the current step
+        self._grad_ready: Dict[str, torch.cuda.Event] = {}   # nvls: recorded behind the kernel that produced a big gradient
         self._symm_offsets: Dict[str, int] = {}
         if mode in ("sharded", "nvls") and self.world > 1:
             for k in self.SHARDED_KEYS:
@@ -94,7 +96,9 @@ class GradientExchange:
         for key in sorted(self.sharded):
             shape = tuple(self.master[key].shape)
             n = self.master[key].numel()
-            for tag, dt, nbytes in (("g", torch.float32, 4 * n), ("w", torch.bfloat16, 2 * n)):
+            # the gradient, and TWO operand copies: the fused update of step i writes the copy step i + 1 computes with
+            # while step i's own input-gradient GEMM is still reading the other one
+            for tag, dt, nbytes in (("g", torch.float32, 4 * n), ("w0", torch.bfloat16, 2 * n), ("w1", torch.bfloat16, 2 * n)):
                 plan.append((f"{tag}:{key}", dt, shape, off, nbytes))
                 off += (nbytes + 255) // 256 * 256
         arena = symm_mem.empty(off, dtype=torch.uint8, device=dev)
@@ -114,6 +118,15 @@ class GradientExchange:
         t = self.symm_tensors[name]
         return int(self.symm.multicast_ptr) + self._symm_offsets[name] + row0 * t.stride(0) * t.element_size()
 
+    def operand(self, key: str, slot: Optional[int] = None) -> torch.Tensor:
+        return self.symm_tensors[f"w{self.operand_slot if slot is None else slot}:{key}"]
+
+    def wait_big_gradients(self) -> None:
+        """Orders the current stream behind the kernels that produced the big weight gradients of this step."""
+        for ev in self._grad_ready.values():
+            torch.cuda.current_stream().wait_event(ev)
+        self._grad_ready.clear()
+
     def barrier(self) -> None:
         """Cross-rank barrier on the current stream (signal pads of the symmetric arena; no host synchronisation)."""
         self.symm.barrier(channel=0)
@@ -127,6 +140,9 @@ class GradientExchange:
             # the ranks' sum through the switch
             if grad.data_ptr() != self.symm_tensors[f"g:{key}"].data_ptr() + row0 * grad.stride(0) * 4:
                 raise RuntimeError(f"GradientExchange(nvls): the gradient of {key} was not produced in the symmetric buffer")
+            ev = torch.cuda.Event()
+            ev.record()          # the update stream waits for THIS, not for the end of the backward
+            self._grad_ready[key] = ev
             self.bytes_last_step["nvls_ld_reduce"] = self.bytes_last_step.get("nvls_ld_reduce", 0) + grad.numel() * 4 // self.world
             self.bytes_last_step["nvls_multicast_store"] = self.bytes_last_step.get("nvls_multicast_store", 0) + grad.numel() * 2 // self.world
             return

@@ -288,7 +288,8 @@ class OICRPlusHeads(nn.Module):
             # the engine writes the big weight gradients straight into the symmetric buffers (one launch each: no row
             # panels, nothing to overlap) and computes with the symmetric operands the fused update broadcasts into
             eng.external_grad_bufs.update({k: ex.symm_tensors[f"g:{k}"] for k in ex.sharded})
-            eng.op.adopt_operand_storage(w6=ex.symm_tensors.get("w:fc1_w"), w7=ex.symm_tensors.get("w:fc2_w"))
+            eng.op.adopt_operand_storage(w6=ex.operand("fc1_w") if "fc1_w" in ex.sharded else None,
+                                         w7=ex.operand("fc2_w") if "fc2_w" in ex.sharded else None)
             eng.fc1_wgrad_panels = 1
         self.engine()
         return self.exchange

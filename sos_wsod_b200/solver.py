@@ -120,19 +120,47 @@ class B200SGD(torch.optim.Optimizer):
         update_stream = exchanges[0][1].update_stream() if exchanges else None
         if update_stream is not None and os.environ.get("SOSWSOD_UPDATE_ON_MAIN"):      # diagnosis: serialise the update
             update_stream = torch.cuda.current_stream()
+        ready = None
         if update_stream is not None:
             ready = torch.cuda.Event()
             ready.record()                       # every gradient kernel of the step is queued behind this point
-            update_stream.wait_event(ready)
         ctx = torch.cuda.stream(update_stream) if update_stream is not None else contextlib.nullcontext()
         nvls_items, nvls_params = [], set()
+        for h, ex in exchanges:
+            for key in sorted(ex.sharded):
+                if ex.mode == "nvls":
+                    nvls_params.add(id(ex.master[key]))
+        if nvls_params:
+            # nvls: the big matrices first, behind nothing but the kernels that produced their gradients (the host is
+            # milliseconds ahead of the device: this is queued while the backward is still running, and the update kernel
+            # shares the SMs with the input-gradient GEMM)
+            with ctx:
+                for group in self.param_groups:
+                    for p in group["params"]:
+                        if id(p) not in nvls_params or p.grad is None:
+                            continue
+                        ex, key = key_of[id(p)]
+                        ex.check_gradient_buffer(key, p.grad)
+                        st = self.state[p]
+                        if "momentum_buffer" not in st:
+                            st["momentum_buffer"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
+                        lo, hi = ex.owned_rows_nvls(key)
+                        nvls_items.append((float(group["momentum"]), ex,
+                                           (p.detach()[lo:hi], ex.multicast_address(f"g:{key}", lo), st["momentum_buffer"][lo:hi],
+                                            ex.multicast_address(f"w{ex.operand_slot ^ 1}:{key}", lo), group["lr"], group["weight_decay"])))
+                if nvls_items:
+                    ex = nvls_items[0][1]
+                    ex.wait_big_gradients()
+                    ex.barrier()             # every rank's weight gradients are complete in the symmetric buffers
+                    for momentum in sorted({m for m, _, _ in nvls_items}):
+                        self.launches_last_step += ops.sgd_nvls([it for m, _, it in nvls_items if m == momentum], momentum, 1.0 / ex.world)
+        if update_stream is not None:
+            update_stream.wait_event(ready)
         with ctx:
             for h, ex in exchanges:
                 ex.wait_gradients()
                 for key in sorted(ex.sharded):
                     shard_rows[id(ex.master[key])] = ex.owned_rows(key)
-                    if ex.mode == "nvls":
-                        nvls_params.add(id(ex.master[key]))
             by_momentum, touched = {}, []          # the reference makes one group per parameter: batch across groups
             for group in self.param_groups:
                 for p in group["params"]:
@@ -153,12 +181,7 @@ class B200SGD(torch.optim.Optimizer):
                     ob, of = sinks.get(id(p), (None, None))
                     items = by_momentum.setdefault(float(group["momentum"]), [])
                     pd, buf = p.detach(), st["momentum_buffer"]
-                    if id(p) in nvls_params:
-                        # fused reduce-scatter + update + all-gather over NVSwitch multicast: this rank's rows only
-                        ex, key = key_of[id(p)]
-                        lo, hi = ex.owned_rows_nvls(key)
-                        nvls_items.append((float(group["momentum"]), ex, (pd[lo:hi], ex.multicast_address(f"g:{key}", lo), buf[lo:hi],
-                                                                          ex.multicast_address(f"w:{key}", lo), group["lr"], group["weight_decay"])))
+                    if id(p) in nvls_params:       # done above by the fused reduce + update + broadcast kernel
                         touched.append(p)
                         continue
                     for lo, hi in shard_rows.get(id(p), [(0, p.size(0) if p.dim() else 1)]):
@@ -166,11 +189,6 @@ class B200SGD(torch.optim.Optimizer):
                         sl = (lambda t: t) if whole else (lambda t, lo=lo, hi=hi: None if t is None else t[lo:hi])
                         items.append((sl(pd), sl(grad), sl(buf), group["lr"], group["weight_decay"], sl(ob), sl(of)))
                     touched.append(p)
-            if nvls_items:
-                ex = nvls_items[0][1]
-                ex.barrier()             # every rank's weight gradients are complete in the symmetric buffers
-                for momentum in sorted({m for m, _, _ in nvls_items}):
-                    self.launches_last_step += ops.sgd_nvls([it for m, _, it in nvls_items if m == momentum], momentum, 1.0 / ex.world)
             for momentum, items in by_momentum.items():
                 self.launches_last_step += ops.sgd_multi(items, momentum)
             if nvls_items:
@@ -178,6 +196,13 @@ class B200SGD(torch.optim.Optimizer):
             for h, ex in exchanges:
                 if ex.mode == "nvls":
                     ex.master_stale = True
+                    if nvls_items:       # from the next launch on, the engine computes with the copies just written
+                        ex.operand_slot ^= 1
+                        op = h.engine().op
+                        if "fc1_w" in ex.sharded:
+                            op.w6 = ex.operand("fc1_w")
+                        if "fc2_w" in ex.sharded:
+                            op.w7 = ex.operand("fc2_w")
                 else:
                     op = h.engine().op
                     ex.gather_operands({"fc1_w": op.w6, "fc2_w": op.w7})
