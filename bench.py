@@ -321,6 +321,7 @@ def run_b200_arm(args):
     master = eng.op.master
     eng.fc1_wgrad_panels = int(os.environ.get("SOSWSOD_FC1_PANELS", eng.fc1_wgrad_panels))
     eng.fc1_wgrad_position = os.environ.get("SOSWSOD_FC1_WGRAD_POS", eng.fc1_wgrad_position)
+    ops.NVLS_MAX_CTAS = int(os.environ.get("SOSWSOD_NVLS_CTAS", ops.NVLS_MAX_CTAS))
     n_img = 3
     host = make_host_images(n_img, rank)
     dev_imgs = [{"feats": [f.to(dev) for f in im["feats"]], "rois": [r.to(dev) for r in im["rois"]],
