@@ -343,7 +343,7 @@ typedef struct soswsod_sgd_nvls_tensor {
     float weight_decay;
 } soswsod_sgd_nvls_tensor;
 int soswsod_sgd_nvls(const soswsod_sgd_nvls_tensor* tensors, int count, float momentum, float grad_scale,
-                     int max_ctas /* persistent grid size; <= 0: 2 per SM */, soswsod_stream_t stream);
+                     int max_ctas /* persistent grid size; <= 0: 1 per SM */, soswsod_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * (6) PGF, the consumer of the detection-results json.  Replaces the per-image

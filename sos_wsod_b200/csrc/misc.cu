@@ -340,7 +340,7 @@ extern "C" int soswsod_sgd_nvls(const soswsod_sgd_nvls_tensor* tensors, int coun
         chunks += (t.n + kNvlsChunk - 1) / kNvlsChunk;
     }
     b.chunk_start[count] = chunks;
-    if (max_ctas <= 0) max_ctas = 2 * device_num_sms_misc();
+    if (max_ctas <= 0) max_ctas = device_num_sms_misc();
     const long long grid = chunks < max_ctas ? chunks : max_ctas;
     sgd_nvls_kernel<<<(unsigned)grid, kNvlsThreads, 0, (cudaStream_t)stream>>>(b);
     SOSWSOD_CHECK_LAUNCH();

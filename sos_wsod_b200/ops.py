@@ -307,7 +307,7 @@ def sgd_multi(items, momentum: float, grad_scale: float = 1.0) -> int:
     return n_launch
 
 
-NVLS_MAX_CTAS = 0      # persistent grid of the fused NVLS update; 0 = the library default (2 per SM)
+NVLS_MAX_CTAS = 0      # persistent grid of the fused NVLS update; 0 = the library default (1 per SM)
 
 
 def sgd_nvls(items, momentum: float, grad_scale: float) -> int:
