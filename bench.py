@@ -318,6 +318,8 @@ def run_b200_arm(args):
             ex = heads.set_gradient_exchange(mode=mode)
     eng = heads.engine()
     opt = build_optimizer(cfg, heads)
+    if os.environ.get("SOSWSOD_NO_OVERLAP_UPDATE"):      # A/B: the single-GPU update after the step instead of under it
+        opt.overlap_update = False
     master = eng.op.master
     eng.fc1_wgrad_panels = int(os.environ.get("SOSWSOD_FC1_PANELS", eng.fc1_wgrad_panels))
     eng.fc1_wgrad_position = os.environ.get("SOSWSOD_FC1_WGRAD_POS", eng.fc1_wgrad_position)
@@ -482,6 +484,10 @@ def run_b200_arm(args):
     ops.sgd_multi = timed(sgd_events, orig_sgd)
     ops.sgd_nvls = timed(nvls_events, orig_nvls)
     ev_steps = max(5, min(20, K_steps))
+    # single GPU: in the timed blocks the optimizer update runs UNDER the fc6 input-gradient GEMM and the ROI backward
+    # (solver.B200SGD._overlapped_head_update); here it is put back behind the step so that every kernel is timed alone
+    overlap_in_timed_blocks = bool(getattr(opt, "overlapped_last_step", False))
+    overlap_setting, opt.overlap_update = opt.overlap_update, False if world == 1 else opt.overlap_update
     for i in range(3):          # the event pass's own allocation pattern, untimed
         device_step(1900 + i)
     sync_all()
@@ -501,6 +507,7 @@ def run_b200_arm(args):
     sync_all()
     sampler.window(w0, time.perf_counter())
     ev_pass_ms_per_step = ea.elapsed_time(eb) / ev_steps
+    opt.overlap_update = overlap_setting
     ops.gemm_bf16, ops.roi_pool_forward, ops.roi_pool_backward, ops.sgd_multi, ops.sgd_nvls = orig_gemm, orig_fwd, orig_bwd, orig_sgd, orig_nvls
 
     tot_flops = sum(e[2] for e in gemm_events)
@@ -571,7 +578,13 @@ def run_b200_arm(args):
     roofline["sgd_step"] = {"ms_per_step": sgd_ms, "launches_per_step": len(sgd_events) // ev_steps, "bytes": sgd_bytes,
                             "hbm_gbs": sgd_bytes / (sgd_ms * 1e-3) / 1e9 if sgd_ms > 0 else 0.0,
                             "frac_of_hbm_peak": (sgd_bytes / (sgd_ms * 1e-3) / 1e9) / peaks["hbm_gbs"] if sgd_ms > 0 else 0.0,
-                            "bound": "hbm", "params": n_params, "rows_updated_fraction": shard}
+                            "bound": "hbm", "params": n_params, "rows_updated_fraction": shard,
+                            "overlapped_in_timed_blocks": overlap_in_timed_blocks,
+                            "note": ("timed blocks and e2e: queued behind the fc6 weight-gradient GEMM on a second stream, it runs "
+                                     "UNDER the fc6 input-gradient GEMM and the ROI backward (power-capped device: -0.08 ms per "
+                                     "step, profiles/r02_overlap_ab.log); this event pass: serialised behind the step, so every "
+                                     "kernel above is timed alone")
+                            if overlap_in_timed_blocks else "runs alone after the step's last kernel"}
     if nvls_events:
         nv_ms = sum(e0.elapsed_time(e1) for e0, e1 in nvls_events) / ev_steps
         big = sum(master[k].numel() for k in ex.sharded)

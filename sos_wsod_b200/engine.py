@@ -86,6 +86,7 @@ class HeadOperands:
         self.w7 = torch.empty(fc2_w.shape, dtype=torch.bfloat16, device=dev)
         self.wh = torch.zeros((cfg.head_cols_padded, cfg.fc_dim), dtype=torch.bfloat16, device=dev)
         self.bh = torch.zeros((cfg.head_cols_padded,), dtype=torch.float32, device=dev)
+        self._w6_spare = None       # second fc6 operand buffer, see spare_w6()
         self._versions = None
         self.pre_refresh = None     # callable run before a re-cast (a sharded optimizer brings the fp32 masters up to date)
         self.refresh()
@@ -119,6 +120,16 @@ class HeadOperands:
                 assert t.shape == cur.shape and t.dtype == cur.dtype and t.device == cur.device
                 t.copy_(cur)
                 setattr(self, name, t)
+
+    def spare_w6(self) -> torch.Tensor:
+        """A second buffer for the fc6 operand: an optimizer that runs UNDER the step's input-gradient GEMM (which still
+        reads `w6`) writes the refreshed operand here and then calls swap_w6()."""
+        if self._w6_spare is None:
+            self._w6_spare = torch.empty_like(self.w6)
+        return self._w6_spare
+
+    def swap_w6(self) -> None:
+        self.w6, self._w6_spare = self._w6_spare, self.w6
 
     def mark_fresh(self) -> None:
         """Declares the operands up to date with the master parameters as they are now -- called by an optimizer that
@@ -198,6 +209,12 @@ class OICRPlusHeadEngine:
         self._grad_bufs: Dict[str, torch.Tensor] = {}
         self.external_grad_bufs: Dict[str, torch.Tensor] = {}     # "fc1_w" / "fc2_w" / "head_w" -> caller-owned fp32 buffers
         self._side_stream = None
+        # set by every train_step that ran single-GPU with dW6 first: the events behind which EVERY parameter gradient
+        # of the step is complete (while the input-gradient GEMM and the ROI backward are still running) and the identity
+        # (address, version counter) of each gradient tensor -- solver.B200SGD runs the update under those kernels if
+        # `.grad` is still exactly what the step produced
+        self.publish_grad_events = True
+        self.early_grads: Optional[dict] = None
 
     def _operands_ready(self):
         """Called between the ROI pooling (which needs no weights) and the first GEMM: an operand all-gather of the
@@ -381,8 +398,22 @@ class OICRPlusHeadEngine:
             return dW6, db6
 
         pos = self.fc1_wgrad_position if need_feat_grad else "first"
+        early_events = None
+        self.early_grads = None
         if pos == "first":
             dW6, db6 = weight_gradient()
+            if grad_hook is None and need_feat_grad and self.publish_grad_events:
+                # every parameter gradient is queued (this stream up to here, bias sums on the side stream)
+                if side is not None:
+                    with torch.cuda.stream(side):
+                        dbh = dbh_raw * col_scale
+                        ev_side = torch.cuda.Event()
+                        ev_side.record()
+                else:
+                    dbh = dbh_raw * col_scale
+                ev_main = torch.cuda.Event()
+                ev_main.record()
+                early_events = [ev_main] + ([ev_side] if side is not None else [])
         if need_feat_grad:
             dX = input_gradient()
             self.launches_last_step += 1
@@ -395,12 +426,14 @@ class OICRPlusHeadEngine:
         self.launches_last_step += 9
         if side is not None:
             torch.cuda.current_stream().wait_stream(side)
-        if grad_hook is None:
+        if grad_hook is None and early_events is None:
             dbh = dbh_raw * col_scale
         grads = {"fc1_w": dW6, "fc1_b": db6, "fc2_w": dW7, "fc2_b": db7}
         for wk, bk, r0, n in op.head_slices():
             grads[wk] = dWh[r0:r0 + n]
             grads[bk] = dbh[r0:r0 + n]
+        if early_events is not None:
+            self.early_grads = {"events": early_events, "ident": {k: (g.data_ptr(), g._version) for k, g in grads.items()}}
         aux = {"scores": scores, "img_scores": img_scores, "prev": prev, "logits": L, "x": H7, "acc_counts": acc,
                "view_losses": view_losses, "wsddn_view_losses": wloss}
         aux.update(mined)

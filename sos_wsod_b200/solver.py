@@ -69,6 +69,11 @@ class B200SGD(torch.optim.Optimizer):
         super().__init__(params, dict(lr=lr, momentum=momentum, weight_decay=weight_decay))
         self._heads = []
         self.launches_last_step = 0
+        # single GPU: run the update of an attached head UNDER the step's input-gradient GEMM and ROI backward (see
+        # _overlapped_head_update); False = always on the caller's stream after everything
+        self.overlap_update = True
+        self.overlapped_last_step = False
+        self._update_stream = None
 
     def attach_head(self, heads) -> "B200SGD":
         """heads: an OICRPlusHeads whose parameters this optimizer updates.  If the head exchanges its gradients
@@ -92,6 +97,60 @@ class B200SGD(torch.optim.Optimizer):
                 if "momentum_buffer" in st:
                     ex.gather_rows(st["momentum_buffer"], key)
 
+    def _overlapped_head_update(self, sinks) -> Set[int]:
+        """Single-GPU heads.  The engine queues the weight gradient of fc6 BEFORE the input-gradient GEMM and the ROI
+        backward (2.2 of the step's 7 ms, tensor- and shared-memory-bound), and publishes the events behind which every
+        parameter gradient is complete.  The host reaches optimizer.step() while the device is still milliseconds
+        behind, so the whole update of the head (HBM-bound, 2.7 GB) is queued on a second stream behind those events
+        and runs under those kernels; the refreshed fc6 operand goes to a spare buffer (the input-gradient GEMM still
+        reads the current one) and the two swap.  The caller's stream waits for the update before anything else it is
+        given, so every later reader of the parameters is ordered as if the update had run in place.
+        Only if every `.grad` is still EXACTLY the tensor the step produced (same address, same version counter: no
+        accumulation, rescaling, clipping in between); otherwise nothing is done here and step() updates as usual.
+        Returns the ids of the parameters updated."""
+        done: Set[int] = set()
+        self.overlapped_last_step = False
+        for h in self._heads:
+            ex = getattr(h, "exchange", None)
+            eng = h.engine()
+            early, eng.early_grads = eng.early_grads, None       # one use: a later step() without a new backward finds nothing
+            if early is None or not self.overlap_update or (ex is not None and ex.world > 1):
+                continue
+            master = eng.op.master
+            if any(p.grad is None or (p.grad.data_ptr(), p.grad._version) != early["ident"][k] or not p.grad.is_contiguous()
+                   or not p.is_contiguous() for k, p in master.items()):
+                continue
+            group_of = {id(p): g for g in self.param_groups for p in g["params"]}
+            if any(id(p) not in group_of for p in master.values()):
+                continue
+            if self._update_stream is None:
+                self._update_stream = torch.cuda.Stream(device=master["fc1_w"].device)
+            us = self._update_stream
+            for ev in early["events"]:
+                us.wait_event(ev)
+            by_momentum = {}
+            with torch.cuda.stream(us):
+                for k, p in master.items():
+                    g = group_of[id(p)]
+                    st = self.state[p]
+                    if "momentum_buffer" not in st:
+                        st["momentum_buffer"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
+                    p.grad.record_stream(us)       # `.grad` may be dropped by the host before the update ran
+                    ob, of = sinks.get(id(p), (None, None))
+                    if k == "fc1_w":
+                        ob = eng.op.spare_w6()
+                    by_momentum.setdefault(float(g["momentum"]), []).append(
+                        (p.detach(), p.grad, st["momentum_buffer"], g["lr"], g["weight_decay"], ob, of))
+                    done.add(id(p))
+                for momentum, items in by_momentum.items():
+                    self.launches_last_step += ops.sgd_multi(items, momentum)
+                finished = torch.cuda.Event()
+                finished.record()
+            eng.op.swap_w6()
+            torch.cuda.current_stream().wait_event(finished)
+            self.overlapped_last_step = True
+        return done
+
     def _sinks(self):
         out = {}
         for h in self._heads:
@@ -106,6 +165,7 @@ class B200SGD(torch.optim.Optimizer):
                 loss = closure()
         sinks = self._sinks()
         self.launches_last_step = 0
+        updated_early = self._overlapped_head_update(sinks)
         # Data-parallel heads: the rest of the exchange runs on the exchange's UPDATE STREAM -- wait for the gradient
         # collectives, update (a sharded parameter only on the rows this rank owns: their averaged gradient arrived by
         # reduce-scatter), all-gather the bf16 operand rows -- while the compute stream goes on to the next step's ROI
@@ -165,6 +225,9 @@ class B200SGD(torch.optim.Optimizer):
             for group in self.param_groups:
                 for p in group["params"]:
                     if p.grad is None:
+                        continue
+                    if id(p) in updated_early:
+                        touched.append(p)
                         continue
                     if not p.is_cuda:
                         raise RuntimeError("B200SGD steps CUDA parameters only (sm_100a kernel); there is no CPU fallback")

@@ -611,6 +611,66 @@ def test_b200_sgd_attached_writes_operands_in_the_update_pass(cuda_lib):
         ops.cast_f32_bf16 = orig
 
 
+def test_b200_sgd_update_under_the_backward_is_bit_identical(cuda_lib):
+    """Single GPU: with feature-map gradients requested the engine queues dW6 before dX / ROI backward and B200SGD runs
+    the head's update on a second stream under those kernels (spare fc6 operand buffer, swapped).  Same bits as the
+    update run after the step; any touch of `.grad` in between (here an in-place multiply by one) turns it off."""
+    import copy
+
+    from sos_wsod_b200.config import get_cfg
+    from sos_wsod_b200.modeling import build_roi_heads
+    from sos_wsod_b200.solver import build_optimizer
+    from sos_wsod_b200.structures import Boxes, Instances, ShapeSpec
+
+    torch.manual_seed(0)
+    cfg = get_cfg()
+    cfg.MODEL.ROI_BOX_HEAD.DAN_DIM = [256, 256]
+    ch, R = 32, 160
+    heads = build_roi_heads(cfg, {"plain5": ShapeSpec(channels=ch, stride=8)}).cuda().train()
+    init = copy.deepcopy(heads.state_dict())
+    g = torch.Generator().manual_seed(3)
+    views = ref.synth_views(R, [(240, 320), (288, 384)], g, channels=ch)
+    f1 = torch.cat([views[0].feat, views[1].feat], 0).cuda().requires_grad_(True)
+    f2 = torch.cat([views[2].feat, views[3].feat], 0).cuda().requires_grad_(True)
+    props = [[Instances(v.image_size, proposal_boxes=Boxes(v.boxes.cuda()), objectness_logits=v.obj.cuda())] for v in views]
+    targets = [Instances(views[0].image_size, gt_classes=torch.tensor([2, 9]).cuda(), gt_boxes=Boxes(torch.zeros(2, 4).cuda()))]
+
+    def run(overlap, touch):
+        heads.load_state_dict(init)
+        heads.iter = 0
+        opt = build_optimizer(cfg, heads)
+        opt.overlap_update = overlap
+        flags, fgrads = [], []
+        for _ in range(3):
+            opt.zero_grad()
+            f1.grad = f2.grad = None
+            _, losses = heads(None, [{"plain5": f1}, {"plain5": f2}], props, [targets, None, None, None])
+            sum(losses.values()).backward()
+            if touch:
+                heads.box_head.fc2.bias.grad.mul_(1.0)
+            opt.step()
+            flags.append(opt.overlapped_last_step)
+            fgrads.append((f1.grad.clone(), f2.grad.clone()))
+        torch.cuda.synchronize()
+        op = heads.engine().op
+        return ({k: v.detach().clone() for k, v in heads.state_dict().items()}, op.w6.clone(), op.w7.clone(), op.wh.clone(),
+                op.bh.clone(), flags, fgrads)
+
+    base = run(False, False)
+    over = run(True, False)
+    touched = run(True, True)
+    assert base[5] == [False] * 3 and over[5] == [True] * 3 and touched[5] == [False] * 3
+    for other in (over, touched):
+        for k in base[0]:
+            assert torch.equal(base[0][k], other[0][k]), k
+        for i in range(1, 5):
+            assert torch.equal(base[i], other[i]), i
+        for (a1, a2), (b1, b2) in zip(base[6], other[6]):
+            assert torch.equal(a1, b1) and torch.equal(a2, b2)
+    op = heads.engine().op
+    assert torch.equal(op.w6, heads.box_head.fc1.weight.detach().to(torch.bfloat16))
+
+
 def test_sgd_multi_matches_torch_sgd(cuda_lib):
     """soswsod_sgd_multi over ragged tensors (sizes not multiples of 4, unaligned views, shards) == torch.optim.SGD."""
     from sos_wsod_b200 import ops
