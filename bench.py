@@ -1008,6 +1008,55 @@ def run_detect_arm(args):
     sampler.window(w0, time.perf_counter())
     clocks = sampler.stop()
     launches = ops.COUNTERS["launches"] - n0
+    # ---- untimed: where the device time of an image goes (CUDA events around every operator call of 8 images) ----
+    stage_names = ["tta_views", "roi_pool_plan", "roi_pool_forward", "gemm_bf16", "predict", "tta_merge", "detect"]
+    stage_events = {n: [] for n in stage_names}
+    originals = {n: getattr(ops, n) for n in stage_names}
+
+    def staged(name):
+        orig = originals[name]
+
+        def fn(*a, **kw):
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record()
+            out = orig(*a, **kw)
+            a1.record()
+            fl = 0.0
+            if name == "gemm_bf16":
+                fl = 2.0 * a[0].shape[0] * a[0].shape[1] * (a[1].shape[1] if kw.get("b_mn") else a[1].shape[0])
+            stage_events[name].append((a0, a1, fl))
+            return out
+        return fn
+
+    split_images = 8
+    try:
+        for n in stage_names:
+            setattr(ops, n, staged(n))
+        for i in range(2):
+            one_image(i, sets[0][0], 0)
+        torch.cuda.synchronize()
+        for v in stage_events.values():
+            v.clear()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for i in range(split_images):
+            one_image(i, sets[0][0], 0)
+        s1.record()
+        torch.cuda.synchronize()
+    finally:
+        for n in stage_names:
+            setattr(ops, n, originals[n])
+    split_total = s0.elapsed_time(s1) / split_images
+    stages = {}
+    for n, evs in stage_events.items():
+        t = sum(a0.elapsed_time(a1) for a0, a1, _ in evs) / split_images
+        stages[n] = {"ms_per_image": t, "calls_per_image": len(evs) / split_images, "share": t / split_total}
+        if n == "gemm_bf16":
+            stages[n]["tflops"] = sum(f for _, _, f in evs) / split_images / (t * 1e-3) / 1e12
+    stages["detect"]["kernels"] = "threshold + per-class sort (nms_sort) + IoU bitmask (nms_mask) + scan (nms_scan) + top-k merge"
+    stages["_pass"] = {"images": split_images, "ms_per_image": split_total,
+                       "other_ms_per_image": split_total - sum(v["ms_per_image"] for k, v in stages.items() if k != "_pass"),
+                       "note": "untimed pass after the job; events around every operator call on the compute stream"}
     tm = torch.tensor([dev_ms, wall_s * 1e3, t_gen * 1e3], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tm, op=dist.ReduceOp.MAX)
@@ -1024,7 +1073,7 @@ def run_detect_arm(args):
                 "image_views_per_s": value * V, "proposals_per_s": value * V * R,
                 "device_ms_per_image_rank_max": dev_ms / len(mine), "images_per_rank": len(mine),
                 "generation_s_rank_max": gen_ms / 1e3, "gather_and_json_dump_s": (wall_ms - gen_ms) / 1e3,
-                "generation_images_per_s": args.images / (gen_ms / 1e3),
+                "generation_images_per_s": args.images / (gen_ms / 1e3), "stages": stages,
                 "config": {"workload": f"cfg5: test-time detection-result generation, {args.images} synthetic 480x640 images sharded "
                                        f"by InferenceSampler blocks over {world} GPU(s), {V} views ({len(scales)} scales x h-flip) x {R} "
                                        f"proposals, C={C}, K={REFINE_K}: proposal transform -> ROI pool + fc6/fc7 + heads (all views, one "
