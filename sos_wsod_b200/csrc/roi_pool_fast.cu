@@ -356,6 +356,284 @@ roi_pool_fwd_fast_kernel(const float* __restrict__ feat, int C, int H, int W, co
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// forward, "half table" layout: maps whose two interleaved planes + full window table do not fit one SM's shared
+// memory (96x128, 108x144: the large test-time views).  The 1 x 4 window table is kept for EVEN window starts only
+// and lives next to its plane row: a row is [W cells][W/2 window entries] (pitch 1.5 W cells, W even), so one row
+// pointer serves both and a load is named by its COLUMN in that row (col < W: the cell itself, col >= W: the window
+// starting at cell 2 (col - W)).  A bin row [ws, we) is covered, left to right, by
+//     [cell ws if ws is odd]  windows at even starts a, a+4, .., b (b = the last even start with b+4 <= we)  [cell we-1]
+// (no window fits a 4-wide bin at an odd start: its cells are read one by one); lanes with a shorter list repeat their
+// last load.  Loads only ever cover cells of the bin and are visited left to right, and a re-read never wins the strict
+// '>': value and arg-max are torchvision's, as in the full-table kernel.  The winner is recorded as (row << 8 | col).
+// (Four channels at a time never pay here: wherever they fit with the half table, two fit with the full table, which
+// needs a third fewer loads per bin row -- measured 687 vs 708 us at 72x96.)
+struct BinCols {
+    int mode, ws, we, W, hd, a, bb, nw, cend;
+    __device__ __forceinline__ BinCols(int mode_, int ws_, int we_, int W_) : mode(mode_), ws(ws_), we(we_), W(W_) {
+        hd = ws & 1;
+        a = ws + hd;
+        bb = (we - 4) & ~1;
+        nw = (mode == 1 && bb >= a) ? ((bb - a + 3) >> 2) + 1 : 0;
+        cend = nw ? bb + 4 : a;
+    }
+    __device__ __forceinline__ int count() const { return hd + nw + (we - cend); }      // mode 1
+    __device__ __forceinline__ int col(int t) const {
+        if (mode == 0) return max(min(ws + t, we - 1), ws);
+        if (t < hd) return ws;
+        const int k = t - hd;
+        if (k < nw) return W + (min(a + 4 * k, bb) >> 1);
+        return min(cend + (k - nw), we - 1);
+    }
+};
+
+template <int CI>
+__device__ __forceinline__ void half_store(const float (&m)[CI], const int (&pos)[CI], bool empty, const uint8_t* __restrict__ otab,
+                                           int W, float scl, uint32_t* __restrict__ sp) {
+#pragma unroll
+    for (int c = 0; c < CI; ++c) {
+        float outv = empty ? 0.f : -FLT_MAX;
+        int idx = -1;
+        if (pos[c] >= 0) {
+            outv = m[c];
+            const int hh = pos[c] >> 8, cc = pos[c] & 255;
+            if (cc >= W) {
+                idx = hh * W + ((cc - W) << 1);
+                idx += otab[(idx >> 1) * CI + c];
+            } else {
+                idx = hh * W + cc;
+            }
+        }
+        sp[c * kPP] = pack_out(outv, scl, idx);
+    }
+}
+
+#define SOSWSOD_HALF_UPDATE(COLV)                                \
+    {                                                            \
+        float v[CI];                                             \
+        ld_cell<CI>(v, src + (COLV) * CI);                       \
+        const int code = rowcode + (COLV);                       \
+        _Pragma("unroll") for (int c = 0; c < CI; ++c)           \
+            if (v[c] > m[c]) {                                   \
+                m[c] = v[c];                                     \
+                pos[c] = code;                                   \
+            }                                                    \
+    }
+
+// both steps (bin rows sub and sub + 4) of a roi with the lane's NS loads per bin row
+template <int CI, int NS>
+__device__ __forceinline__ void pool_roi_cols(const float* __restrict__ rows, const uint8_t* __restrict__ otab, int pitch,
+                                              int W, const BinCols& bc, uint32_t hb0, uint32_t hb1, int sub, int pw,
+                                              bool active, int bw, float scl, uint32_t* __restrict__ sp) {
+    int col[NS];
+#pragma unroll
+    for (int t = 0; t < NS; ++t) col[t] = bc.col(t);
+#pragma unroll 1
+    for (int s = 0; s < 2; ++s) {
+        const int ph = sub + 4 * s;
+        const bool on = active && ph < kPlanP;
+        const uint32_t hb = s ? hb1 : hb0;
+        const int hs = (int)(hb & 0xFFFFu), he = (int)(hb >> 16);
+        const int nrows = (on && bw > 0) ? he - hs : 0;
+        const int nrmax = (int)__reduce_max_sync(FULL_MASK, (unsigned)nrows);
+        if (!on) continue;
+        float m[CI];
+        int pos[CI];
+#pragma unroll
+        for (int c = 0; c < CI; ++c) {
+            m[c] = -FLT_MAX;
+            pos[c] = -1;
+        }
+        const float* src = rows + hs * pitch;
+        int rowcode = hs << 8;
+        for (int h = 0; h < nrmax; ++h, src += pitch, rowcode += 256) {
+            if (h < nrows) {
+#pragma unroll
+                for (int t = 0; t < NS; ++t) SOSWSOD_HALF_UPDATE(col[t])
+            }
+        }
+        half_store<CI>(m, pos, nrows <= 0, otab, W, scl, sp + ph * kPlanP + pw);
+    }
+}
+
+// any bin shape (clipped bins, bins wider than 16 cells, mixed widths): the same cover with per-lane loop bounds
+template <int CI>
+__device__ __forceinline__ void pool_bin_wide(const float* __restrict__ rows, const uint8_t* __restrict__ otab, int pitch,
+                                              int W, int hs, int he, int ws, int we, float scl, uint32_t* __restrict__ sp) {
+    float m[CI];
+    int pos[CI];
+#pragma unroll
+    for (int c = 0; c < CI; ++c) {
+        m[c] = -FLT_MAX;
+        pos[c] = -1;
+    }
+    const bool empty = he <= hs || we <= ws;
+    if (!empty) {
+        const float* src = rows + hs * pitch;
+        int rowcode = hs << 8;
+        for (int h = hs; h < he; ++h, src += pitch, rowcode += 256) {
+            int x = ws;
+            if (x & 1) {
+                SOSWSOD_HALF_UPDATE(x)
+                ++x;
+            }
+            for (; x + 4 <= we; x += 4) SOSWSOD_HALF_UPDATE(W + (x >> 1))
+            for (; x < we; ++x) SOSWSOD_HALF_UPDATE(x)
+        }
+    }
+    half_store<CI>(m, pos, empty, otab, W, scl, sp);
+}
+
+template <int CI>
+__global__ void __launch_bounds__(kFastThreads, 1)
+roi_pool_fwd_half_kernel(const float* __restrict__ feat, int C, int H, int W, const int* __restrict__ img_start,
+                         const int* __restrict__ order, const RoiRecord* __restrict__ rec,
+                         uint16_t* __restrict__ argmax_u16, __nv_bfloat16* __restrict__ out_bf16, long long ld_bf16,
+                         int chunks) {
+    extern __shared__ __align__(16) float smem[];
+    const int HW = H * W;
+    const int pitch = (W + (W >> 1)) * CI;              // floats per row: W cells, then W/2 window entries
+    float* rows = smem;                                 // [H][pitch]
+    uint32_t* stage = reinterpret_cast<uint32_t*>(rows + (size_t)H * pitch);           // [warps][CI * 49]
+    uint8_t* otab = reinterpret_cast<uint8_t*>(stage + kFastWarps * CI * kPP);         // [HW / 2][CI] offset 0..3 of the first maximum
+    const int groups = C / CI;
+    const int b = blockIdx.x / groups;
+    const int c0 = (blockIdx.x % groups) * CI;
+
+    {
+        const float* src = feat + ((size_t)b * C + c0) * HW;
+        for (int i = threadIdx.x; i < HW; i += kFastThreads) {
+            const int h = i / W, x = i - h * W;
+            float v[CI];
+#pragma unroll
+            for (int c = 0; c < CI; ++c) v[c] = __ldg(src + (size_t)c * HW + i);
+            st_cell<CI>(rows + h * pitch + x * CI, v);
+        }
+        __syncthreads();
+        for (int j = threadIdx.x; j < (HW >> 1); j += kFastThreads) {
+            const int i = j << 1;
+            const int h = i / W, x = i - h * W;
+            float* rp = rows + h * pitch;
+            float v[CI];
+            uint32_t o = 0;
+#pragma unroll
+            for (int c = 0; c < CI; ++c) v[c] = -FLT_MAX;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                float u[CI];
+                ld_cell<CI>(u, rp + min(x + k, W - 1) * CI);      // a window cut by the row end is used by no bin
+#pragma unroll
+                for (int c = 0; c < CI; ++c)
+                    if (u[c] > v[c]) {
+                        v[c] = u[c];
+                        o = (o & ~(0xFFu << (8 * c))) | ((uint32_t)k << (8 * c));
+                    }
+            }
+            st_cell<CI>(rp + (W + (x >> 1)) * CI, v);
+            if constexpr (CI == 4) reinterpret_cast<uint32_t*>(otab)[j] = o;
+            else reinterpret_cast<uint16_t*>(otab)[j] = (uint16_t)o;
+        }
+        __syncthreads();
+    }
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int sub = lane / kPlanP, pw = lane - sub * kPlanP;
+    const bool active = lane < 4 * kPlanP;
+    uint32_t* sp = stage + warp * (CI * kPP);
+    constexpr int n_out = CI * kPP;
+
+    const int seg_lo = img_start[b], seg_hi = img_start[b + 1];
+    const int per = (seg_hi - seg_lo + chunks - 1) / chunks;
+    const int lo = seg_lo + blockIdx.y * per;
+    const int hi = min(lo + per, seg_hi);
+    for (int i = lo + warp; i < hi; i += kFastWarps) {
+        const int r = __ldg(order + i);
+        const uint32_t* rw = reinterpret_cast<const uint32_t*>(rec + r);
+        uint32_t hb0 = 0, hb1 = 0, wb = 0;
+        if (active) {
+            hb0 = __ldg(rw + sub);
+            if (sub + 4 < kPlanP) hb1 = __ldg(rw + sub + 4);
+            wb = __ldg(rw + kPlanP + pw);
+        }
+        const float scl = __uint_as_float(__ldg(rw + 15));
+        const int ws = (int)(wb & 0xFFFFu), we = (int)(wb >> 16);
+        const int bw = active ? we - ws : 0;
+        const int bwmax = (int)__reduce_max_sync(FULL_MASK, (unsigned)bw);
+        const int bwmin = (int)__reduce_min_sync(FULL_MASK, active ? (unsigned)bw : 0xFFFFu);
+        // 0: cells one by one (bins <= 4 wide), 1: windows + edge cells with a uniform load count, 2: per-lane loops
+        const int mode = bwmax <= 4 ? 0 : ((bwmax <= 16 && bwmin >= 4) ? 1 : 2);
+        if (mode == 2) {
+            if (active) {
+                pool_bin_wide<CI>(rows, otab, pitch, W, (int)(hb0 & 0xFFFFu), (int)(hb0 >> 16), ws, we, scl, sp + sub * kPlanP + pw);
+                if (sub + 4 < kPlanP)
+                    pool_bin_wide<CI>(rows, otab, pitch, W, (int)(hb1 & 0xFFFFu), (int)(hb1 >> 16), ws, we, scl,
+                                      sp + (sub + 4) * kPlanP + pw);
+            }
+        } else {
+            const BinCols bc(mode, ws, we, W);
+            const int nslots = mode == 0 ? max(bwmax, 1) : (int)__reduce_max_sync(FULL_MASK, (unsigned)(bw > 0 ? bc.count() : 0));
+#define SOSWSOD_COLS(NSV) \
+    case NSV: pool_roi_cols<CI, NSV>(rows, otab, pitch, W, bc, hb0, hb1, sub, pw, active, bw, scl, sp); break;
+            switch (nslots) {
+                SOSWSOD_COLS(1) SOSWSOD_COLS(2) SOSWSOD_COLS(3) SOSWSOD_COLS(4) SOSWSOD_COLS(5) SOSWSOD_COLS(6)
+            }
+#undef SOSWSOD_COLS
+        }
+        __syncwarp();
+        uint16_t* adst = argmax_u16 + ((size_t)r * C + c0) * kPP;
+        uint16_t* vdst = reinterpret_cast<uint16_t*>(out_bf16 + (size_t)r * ld_bf16 + (size_t)c0 * kPP);
+        if (CI == 4) {
+            for (int q = lane; q < n_out / 4; q += 32) {
+                const uint4 w4 = *reinterpret_cast<const uint4*>(sp + 4 * q);
+                uint2 av, vv;
+                av.x = (w4.x & 0xFFFFu) | (w4.y << 16);
+                av.y = (w4.z & 0xFFFFu) | (w4.w << 16);
+                vv.x = (w4.x >> 16) | (w4.y & 0xFFFF0000u);
+                vv.y = (w4.z >> 16) | (w4.w & 0xFFFF0000u);
+                reinterpret_cast<uint2*>(adst)[q] = av;
+                reinterpret_cast<uint2*>(vdst)[q] = vv;
+            }
+        } else {
+            for (int q = lane; q < n_out / 2; q += 32) {
+                const uint2 w2 = *reinterpret_cast<const uint2*>(sp + 2 * q);
+                reinterpret_cast<uint32_t*>(adst)[q] = (w2.x & 0xFFFFu) | (w2.y << 16);
+                reinterpret_cast<uint32_t*>(vdst)[q] = (w2.x >> 16) | (w2.y & 0xFFFF0000u);
+            }
+        }
+        __syncwarp();
+    }
+}
+#undef SOSWSOD_HALF_UPDATE
+
+static int fwd_fast_chunks(int groups, int n, int R) {
+    const int sms = device_num_sms();
+    const int per_img = max(1, R / max(n, 1));
+    const int max_chunks = max(1, min(16, per_img / (2 * kFastWarps)));
+    int chunks = 1;
+    double best = 1e30;
+    for (int ch = 1; ch <= max_chunks; ++ch) {
+        const int waves = (groups * ch + sms - 1) / sms;
+        const double cost = (double)waves / ch + 0.004 * ch;
+        if (cost < best - 1e-9) {
+            best = cost;
+            chunks = ch;
+        }
+    }
+    return chunks;
+}
+
+template <int CI>
+static int launch_fwd_half_ci(const float* feat, int n, int c, int h, int w, int R, const PlanView& pv, uint16_t* a16,
+                              __nv_bfloat16* obf, long long ld, size_t smem, cudaStream_t st) {
+    const int groups = n * (c / CI);
+    const int chunks = fwd_fast_chunks(groups, n, R);
+    auto kern = roi_pool_fwd_half_kernel<CI>;
+    SOSWSOD_ENSURE_SMEM(kern, smem);
+    kern<<<dim3(groups, chunks), kFastThreads, smem, st>>>(feat, c, h, w, pv.img_start, pv.order, pv.rec, a16, obf, ld, chunks);
+    SOSWSOD_CHECK_LAUNCH();
+    return 1;
+}
+
 template <int CI>
 static int launch_fwd_fast_ci(const float* feat, int n, int c, int h, int w, int R, const PlanView& pv, uint16_t* a16,
                               __nv_bfloat16* obf, long long ld, int cells_pad, size_t smem, cudaStream_t st) {
@@ -394,15 +672,19 @@ int launch_fwd_fast(const float* feat, int n, int c, int h, int w, int R, const 
                      ((ld_bf16 * 2) & 7) == 0 && (((long long)c * kPP * 2) & 7) == 0;
     const bool al4 = (reinterpret_cast<uintptr_t>(argmax_u16) & 3) == 0 && (reinterpret_cast<uintptr_t>(out_bf16) & 3) == 0 &&
                      ((ld_bf16 * 2) & 3) == 0 && (((long long)c * kPP * 2) & 3) == 0;
-    {
-        const size_t smem = (size_t)cells_pad * 4 * 4 * 2 + (size_t)kFastWarps * 4 * kPP * 4 + (size_t)cells_pad * 4;
-        if (c % 4 == 0 && al8 && smem <= max_smem)
-            return launch_fwd_fast_ci<4>(feat, n, c, h, w, R, pv, argmax_u16, out_bf16, ld_bf16, cells_pad, smem, st);
+    // four channels per CTA before two; the half table (two channels) only where the full one does not fit
+    auto full_smem = [&](int ci) { return (size_t)cells_pad * ci * 4 * 2 + (size_t)kFastWarps * ci * kPP * 4 + (size_t)cells_pad * ci; };
+    auto half_smem = [&](int ci) { return (size_t)HW * ci * 6 + (size_t)kFastWarps * ci * kPP * 4 + (size_t)(HW / 2) * ci; };
+    const bool half_ok = (w % 2 == 0) && w + w / 2 <= 256 && h <= 255;
+    if (c % 4 == 0 && al8) {
+        if (full_smem(4) <= max_smem)
+            return launch_fwd_fast_ci<4>(feat, n, c, h, w, R, pv, argmax_u16, out_bf16, ld_bf16, cells_pad, full_smem(4), st);
     }
-    {
-        const size_t smem = (size_t)cells_pad * 2 * 4 * 2 + (size_t)kFastWarps * 2 * kPP * 4 + (size_t)cells_pad * 2;
-        if (c % 2 == 0 && al4 && smem <= max_smem)
-            return launch_fwd_fast_ci<2>(feat, n, c, h, w, R, pv, argmax_u16, out_bf16, ld_bf16, cells_pad, smem, st);
+    if (c % 2 == 0 && al4) {
+        if (full_smem(2) <= max_smem)
+            return launch_fwd_fast_ci<2>(feat, n, c, h, w, R, pv, argmax_u16, out_bf16, ld_bf16, cells_pad, full_smem(2), st);
+        if (half_ok && half_smem(2) <= max_smem)
+            return launch_fwd_half_ci<2>(feat, n, c, h, w, R, pv, argmax_u16, out_bf16, ld_bf16, half_smem(2), st);
     }
     return 0;
 }

@@ -190,9 +190,11 @@ def _fast_fwd_check(ops, feat, rois, obj):
 
 
 @pytest.mark.parametrize("C,h,w,R", [(512, 60, 80, 300), (64, 72, 96, 257), (8, 37, 53, 300), (6, 96, 152, 200),
-                                     (4, 20, 200, 150), (2, 150, 30, 100)])
+                                     (4, 20, 200, 150), (2, 150, 30, 100), (8, 108, 144, 300), (16, 96, 128, 300),
+                                     (12, 84, 112, 200), (4, 90, 120, 200)])
 def test_roi_pool_fast_forward_bit_exact(ops, C, h, w, R):
-    """CI=4 and CI=2 interleaves, direct / window-table / generic bin modes (bins up to 200/7 cells wide), clipped,
+    """CI=4 and CI=2 interleaves, full window table (60x80 four channels; 72x96, 84x112, 90x120 two) and half table
+    (96x128, 96x152, 108x144, two channels), direct / window / wide bin modes (bins up to 200/7 cells wide), clipped,
     malformed, out-of-image and empty rois."""
     g = _gen(300 + C + h)
     feat = torch.relu(torch.randn((1, C, h, w), generator=g))
@@ -201,11 +203,13 @@ def test_roi_pool_fast_forward_bit_exact(ops, C, h, w, R):
     _fast_fwd_check(ops, feat, rois, torch.rand(rois.size(0), generator=g))
 
 
-def test_roi_pool_fast_forward_ties_negative_and_batch(ops):
+@pytest.mark.parametrize("h,w", [(45, 64), (72, 96), (100, 140)])
+def test_roi_pool_fast_forward_ties_negative_and_batch(ops, h, w):
     """All-zero channels (every cell ties: the first cell in row-major order must win), negative features, signed
-    zeros, tiny rois (bins narrower than a cell), three images with shuffled roi order and an image without rois."""
+    zeros, tiny rois (bins narrower than a cell), three images with shuffled roi order and an image without rois; on the
+    full-table kernel four (45x64) and two (72x96) channels at a time and on the half-table kernel (100x140)."""
     g = _gen(311)
-    N, C, h, w = 4, 8, 45, 64
+    N, C = 4, 8
     feat = torch.randn((N, C, h, w), generator=g)
     feat[:, 0] = 0.0
     feat[:, 1] = -0.0
@@ -232,6 +236,22 @@ def test_roi_pool_fast_matches_general_kernel_at_bench_shape(ops):
     g = _gen(312)
     feat = torch.relu(torch.randn((2, 512, 72, 96), generator=g)).cuda()
     rois = ref.boxes_to_pooler_format([ref.synth_boxes(2000, 576, 768, g) for _ in range(2)]).cuda()
+    obj = torch.rand(rois.size(0), generator=g).cuda()
+    _, a0, x0 = ops.roi_pool_forward(feat, rois, row_scale=obj, row_scale_bias=1.0, want_f32=False, want_bf16=True, argmax_u16=True)
+    plan = ops.roi_pool_plan(rois, feat.shape, row_scale=obj, row_scale_bias=1.0)
+    _, a1, x1 = ops.roi_pool_forward(feat, rois, row_scale=obj, row_scale_bias=1.0, want_f32=False, want_bf16=True, argmax_u16=True, plan=plan)
+    assert torch.equal(a0, a1)
+    assert torch.equal(x0.view(torch.int16), x1.view(torch.int16))
+
+
+@pytest.mark.parametrize("h,w,scale", [(96, 128, 1.6), (108, 144, 1.8)])
+def test_roi_pool_fast_matches_general_kernel_at_tta_scales(ops, h, w, scale):
+    """The two largest test-time views of BASELINE configs[4] (image + flip, 2 x 2000 proposals scaled with the view):
+    half-table kernel == general kernel, every element."""
+    g = _gen(313)
+    feat = torch.relu(torch.randn((2, 128, h, w), generator=g)).cuda()
+    boxes = [ref.synth_boxes(2000, 480, 640, g) * scale for _ in range(2)]
+    rois = ref.boxes_to_pooler_format(boxes).cuda()
     obj = torch.rand(rois.size(0), generator=g).cuda()
     _, a0, x0 = ops.roi_pool_forward(feat, rois, row_scale=obj, row_scale_bias=1.0, want_f32=False, want_bf16=True, argmax_u16=True)
     plan = ops.roi_pool_plan(rois, feat.shape, row_scale=obj, row_scale_bias=1.0)
