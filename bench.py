@@ -877,6 +877,7 @@ def run_detect_arm(args):
     from sos_wsod_b200.config import get_cfg
     from sos_wsod_b200.engine import ViewBatch
     from sos_wsod_b200.evaluation import PascalVOCDetectionWriter, inference_shard
+    from sos_wsod_b200.evaluation.detection_results import host_gather_group
     from sos_wsod_b200.modeling.test_time_augmentation_avg import DatasetMapperTTAAVG
     from sos_wsod_b200.synthetic import synth_boxes
 
@@ -890,6 +891,7 @@ def run_detect_arm(args):
     _lib.load()
     if world > 1:
         init_dist(dev)
+        host_gather_group()      # the gloo group the detection rows are gathered through (untimed set-up, like the NCCL init)
     heads, cfg = build_heads(dev)
     heads.eval()
     for k in range(heads.refine_K):      # spread the random heads so that detections survive the threshold / NMS
