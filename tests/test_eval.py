@@ -111,6 +111,14 @@ def test_product_writers_are_byte_compatible(gold, tmp_path):
     voc3._predictions[1] += ["9 0.500 10.0 20.0 30.0 40.0"]
     assert voc3.json_text() == _json.dumps(voc3.rows())
     assert PascalVOCDetectionWriter("x", ["a"], "y").json_text() == "[]"
+    # COCO: per-rank encoded pieces joined == json.dump of the chained entries (an empty rank contributes nothing)
+    import itertools
+
+    per_rank = [COCODetectionWriter("c", "p") for _ in range(3)]
+    for i, d in enumerate(per):
+        per_rank[0 if i < 5 else 2].process([{"image_id": d["image_id"]}], [{"instances": _instances(d)}])
+    joined = "[" + ", ".join(t for t in (w.json_piece() for w in per_rank) if t) + "]"
+    assert joined == _json.dumps(list(itertools.chain(*[w._predictions for w in per_rank]))) == gold["coco_json"]
 
 
 _SHARD_SCRIPT = r'''

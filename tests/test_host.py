@@ -390,3 +390,65 @@ def test_solver_param_groups_follow_the_reference_rules():
     cfg.SOLVER.NESTEROV = True
     with pytest.raises(NotImplementedError):
         build_optimizer(cfg, model)
+
+
+def test_half_table_cover_is_exact_for_every_bin_row():
+    """The load list of roi_pool_fwd_half_kernel (csrc/roi_pool_fast.cu, struct BinCols), restated in Python and checked
+    exhaustively: for every bin row [ws, we) of 4..16 cells and every uniform list length up to 6, the loads (single cells
+    and 1 x 4 windows at EVEN starts) touch only cells of the bin, cover all of them, are visited left to right, and the
+    running strict '>' over them returns the value and the FIRST position of the row's maximum -- with heavy ties."""
+    import random
+
+    def cols(ws, we, W, t_count):
+        hd = ws & 1
+        a = ws + hd
+        bb = (we - 4) & ~1
+        nw = ((bb - a + 3) >> 2) + 1 if bb >= a else 0
+        cend = bb + 4 if nw else a
+        count = hd + nw + (we - cend)
+        out = []
+        for t in range(t_count):
+            if t < hd:
+                out.append(ws)
+                continue
+            k = t - hd
+            if k < nw:
+                out.append(W + (min(a + 4 * k, bb) >> 1))
+            else:
+                out.append(min(cend + (k - nw), we - 1))
+        return count, out
+
+    rng = random.Random(7)
+    W = 40
+    for ws in range(0, 20):
+        for bw in range(4, 17):
+            we = ws + bw
+            count, _ = cols(ws, we, W, 0)
+            assert 1 <= count <= 6
+            for ns in range(count, 7):           # a warp pads the lane's list to the longest list among its lanes
+                _, cl = cols(ws, we, W, ns)
+                covered = set()
+                last_first = -1
+                for c in cl:
+                    cells = [c] if c < W else list(range(2 * (c - W), 2 * (c - W) + 4))
+                    assert c < W or (2 * (c - W)) % 2 == 0
+                    assert all(ws <= x < we for x in cells), (ws, we, cl)
+                    assert cells[0] >= last_first, "loads must be visited left to right"
+                    last_first = cells[0]
+                    covered.update(cells)
+                assert covered == set(range(ws, we)), (ws, we, cl)
+                for _ in range(6):
+                    row = [float(rng.randint(0, 3)) for _ in range(W)]      # many ties
+                    best, pos = -1e30, -1
+                    for c in cl:
+                        if c < W:
+                            v, p = row[c], c
+                        else:
+                            x0 = 2 * (c - W)
+                            win = row[x0:x0 + 4]
+                            v = max(win)
+                            p = x0 + win.index(v)                            # the table stores the window's first maximum
+                        if v > best:
+                            best, pos = v, p
+                    seg = row[ws:we]
+                    assert best == max(seg) and pos == ws + seg.index(max(seg)), (ws, we, cl, row[ws:we])
