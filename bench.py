@@ -786,7 +786,8 @@ def run_b200_arm(args):
                                "allreduce": "NCCL all-reduce (AVG) per gradient, async, overlapped with the remaining backward"}[ex.mode])
                            if ex is not None else "none",
                            "allocator": alloc_conf or "default",
-                           "optimizer": "B200SGD (one fused launch: SGD + momentum 0.9 + weight decay 5e-4, bias lr x2; writes the bf16 GEMM operands)",
+                           "optimizer": "B200SGD (one fused launch: SGD + momentum 0.9 + weight decay 5e-4, bias lr x2; writes the bf16 GEMM operands; "
+                                        "single GPU: queued on a second stream under the fc6 input-gradient GEMM and the ROI backward)",
                            "fc_flops_per_step": 3 * 2.0 * VIEWS * R_PROPOSALS * (25088 * 4096 + 4096 * 4096)},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches_per_block), "roofline": roofline,
                 "cpu_baseline": cpu_baseline, "loss": loss_val, "exchange_check": exchange_check}
